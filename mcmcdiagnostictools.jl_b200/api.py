@@ -1,0 +1,524 @@
+"""Host-side mirror of the reference's public interface for the ESS / R-hat hot path.
+
+Same names, keyword arguments, defaults and error behaviour as MCMCDiagnosticTools.jl
+(`ess`, `rhat`, `ess_rhat`, `mcse`, `rhat_nested`, `AutocovMethod`, `FFTAutocovMethod`,
+`BDAAutocovMethod`; /root/reference/src/MCMCDiagnosticTools.jl:19,23), written in Python
+because no Julia toolchain exists in this image; the Julia shim with the identical logic is
+`julia/MCMCDiagB200.jl`.  All numeric work happens in libmcmcdiag_b200.so (hand-written
+sm_100a CUDA) through the C ABI in include/mcmcdiag_b200.h.  There is no CPU fallback.
+
+What stays on the host: `kind` dispatch and the reference's exceptions
+raised before the C call, the `niter <= 4` warning, missing-value masking, Int -> Float64
+promotion, N-d parameter axes and scalar-vs-array outputs (`_maybescalar`), and the
+superchain label -> index matrix of `_validate_superchain_ids`.
+
+Inputs may be NumPy arrays (host memory, staged by the library in overlapped chunks),
+`numpy.ma.MaskedArray` (mask = Julia `missing`), or CUDA `torch.Tensor`s (device memory,
+zero copy when column-major).  Layout is Julia's: shape `(draws, [chains, [params...]])`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+import warnings
+from collections import namedtuple
+from fractions import Fraction
+
+import numpy as np
+
+from . import _lib as L
+
+__all__ = [
+    "ess", "rhat", "ess_rhat", "mcse", "rhat_nested",
+    "AutocovMethod", "FFTAutocovMethod", "BDAAutocovMethod",
+    "ESSMethod", "FFTESSMethod", "BDAESSMethod",
+    "Quantile", "ArgumentError", "DomainError", "DimensionMismatch",
+    "Context", "get_context", "tiedrank", "rank_normalize", "fold_around_median",
+    "generate_ar1", "ESSRhat",
+]
+
+ESSRhat = namedtuple("ESSRhat", ["ess", "rhat"])
+
+
+class ArgumentError(ValueError):
+    """Julia `ArgumentError`."""
+
+
+class DomainError(ValueError):
+    """Julia `DomainError`."""
+
+
+class DimensionMismatch(ValueError):
+    """Julia `DimensionMismatch`."""
+
+
+class AbstractAutocovMethod:
+    """src/ess_rhat.jl:2"""
+    _code = None
+
+
+class AutocovMethod(AbstractAutocovMethod):
+    """Direct biased autocovariance (src/ess_rhat.jl:38, 161-179)."""
+    _code = L.METHODS["direct"]
+
+
+class FFTAutocovMethod(AbstractAutocovMethod):
+    """FFT autocovariance, length nextprod([2,3], 2 niter - 1) (src/ess_rhat.jl:55, 130-152, 181-195)."""
+    _code = L.METHODS["fft"]
+
+
+class BDAAutocovMethod(AbstractAutocovMethod):
+    """BDA variogram estimator (src/ess_rhat.jl:73, 197-213)."""
+    _code = L.METHODS["bda"]
+
+
+# north-star spellings (BASELINE.json) of the same three methods
+ESSMethod, FFTESSMethod, BDAESSMethod = AutocovMethod, FFTAutocovMethod, BDAAutocovMethod
+
+
+class Quantile:
+    """`Base.Fix2(Statistics.quantile, p)` (src/ess_rhat.jl:647)."""
+
+    def __init__(self, p):
+        self.p = p
+
+    def __repr__(self):
+        return f"Quantile({self.p!r})"
+
+
+# ---------------------------------------------------------------------------------------
+# contexts
+# ---------------------------------------------------------------------------------------
+class Context:
+    """Owns one `mcd_ctx` (one per GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = L.load()
+        h = C.c_void_p()
+        rc = self._lib.mcd_create(C.byref(h), int(device))
+        if rc != L.MCD_OK:
+            raise L.MCDLibraryError(
+                f"mcd_create(device={device}) failed ({rc}): {self._lib.mcd_create_error().decode()}")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mcd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- error mapping -------------------------------------------------------------------
+    def check(self, rc: int, domain: bool = False):
+        if rc == L.MCD_OK:
+            return
+        msg = self._lib.mcd_last_error(self._h).decode()
+        if rc == L.MCD_EINVAL:
+            raise (DomainError if domain and "maxlag" in msg else ArgumentError)(msg)
+        if rc == L.MCD_ENAN:
+            raise ArgumentError(msg)
+        if rc == L.MCD_ENOMEM:
+            raise MemoryError(msg)
+        if rc == L.MCD_EUNSUPPORTED:
+            raise NotImplementedError(msg)
+        raise L.MCDLibraryError(f"libmcmcdiag_b200 error {rc}: {msg}")
+
+    def set_option(self, key: str, value: int):
+        self.check(self._lib.mcd_set_option(self._h, key.encode(), int(value)))
+
+    def stat(self, key: str) -> int:
+        return int(self._lib.mcd_get_stat(self._h, key.encode()))
+
+    def set_stream(self, cuda_stream: int | None):
+        self.check(self._lib.mcd_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self.check(self._lib.mcd_synchronize(self._h))
+
+
+_contexts: dict[int, Context] = {}
+_ctx_lock = threading.Lock()
+
+
+def get_context(device: int = 0) -> Context:
+    with _ctx_lock:
+        ctx = _contexts.get(device)
+        if ctx is None:
+            ctx = _contexts[device] = Context(device)
+        return ctx
+
+
+# ---------------------------------------------------------------------------------------
+# array plumbing
+# ---------------------------------------------------------------------------------------
+class _Arr:
+    """A (draws, chains, P) column-major view of the caller's samples + how to build outputs."""
+
+    def __init__(self, samples, min_ndim=1):
+        self.is_torch = type(samples).__module__.startswith("torch")
+        self.missing = None   # boolean per parameter (True = contains missing)
+        if self.is_torch:
+            self._init_torch(samples)
+        else:
+            self._init_numpy(samples)
+
+    # numpy / masked arrays: host memory
+    def _init_numpy(self, samples):
+        mask = None
+        if isinstance(samples, np.ma.MaskedArray):
+            mask = np.ma.getmaskarray(samples)
+            samples = samples.filled(0)
+        x = np.asarray(samples)
+        if x.ndim == 0:
+            raise ArgumentError("samples must have at least one dimension")
+        if x.dtype == np.float32:
+            dt = np.float32
+        elif x.dtype.kind in "fiub":
+            dt = np.float64           # promote_type(eltype, typeof(zero(eltype)/1))
+        else:
+            raise ArgumentError(f"unsupported eltype {x.dtype}")
+        self.dtype = np.dtype(dt)
+        self.pshape = tuple(x.shape[2:])
+        shape3 = (x.shape[0], x.shape[1] if x.ndim > 1 else 1, int(np.prod(self.pshape, dtype=np.int64)))
+        self.draws, self.chains, self.P = shape3
+        self.scalar = x.ndim < 3
+        x3 = np.asfortranarray(x.astype(dt, copy=False)).reshape(shape3, order="F")
+        if mask is not None and mask.any():
+            m3 = np.asfortranarray(mask).reshape(shape3, order="F")
+            self.missing = m3.any(axis=(0, 1))
+            x3 = np.asfortranarray(x3[:, :, ~self.missing])
+        self.x3 = x3
+        self.mem = L.MCD_HOST
+        self.ptr = x3.ctypes.data if x3.size else 0
+        self.nparams = x3.shape[2]
+        self.device = 0
+
+    # torch CUDA tensors: device memory
+    def _init_torch(self, samples):
+        import torch
+        x = samples
+        if not x.is_cuda:
+            raise ArgumentError("torch inputs must be CUDA tensors; pass NumPy arrays for host data")
+        if x.ndim == 0:
+            raise ArgumentError("samples must have at least one dimension")
+        if x.dtype == torch.float32:
+            dt = np.float32
+        elif x.dtype == torch.float64:
+            dt = np.float64
+        else:
+            x = x.to(torch.float64)
+            dt = np.float64
+        self.dtype = np.dtype(dt)
+        self.pshape = tuple(x.shape[2:])
+        self.scalar = x.ndim < 3
+        self.draws = x.shape[0]
+        self.chains = x.shape[1] if x.ndim > 1 else 1
+        self.P = int(np.prod(self.pshape, dtype=np.int64))
+        # column-major <=> the dims-reversed view is C-contiguous
+        xt = x.permute(*reversed(range(x.ndim)))
+        if not xt.is_contiguous():
+            xt = xt.contiguous()
+        self._keep = xt
+        self.torch_dtype = xt.dtype
+        self.torch_device = xt.device
+        self.mem = L.MCD_DEVICE
+        self.ptr = xt.data_ptr()
+        self.nparams = self.P
+        self.device = xt.device.index or 0
+
+    @property
+    def code(self):
+        return L.MCD_F64 if self.dtype == np.float64 else L.MCD_F32
+
+    def new_out(self):
+        if self.is_torch:
+            import torch
+            return torch.empty(self.nparams, dtype=self.torch_dtype, device=self.torch_device)
+        return np.empty(self.nparams, dtype=self.dtype)
+
+    @staticmethod
+    def out_ptr(o):
+        if o is None:
+            return None
+        if isinstance(o, np.ndarray):
+            return C.c_void_p(o.ctypes.data)
+        return C.c_void_p(o.data_ptr())
+
+    def finish(self, o):
+        """Scatter missing parameters back, restore parameter axes, `_maybescalar`."""
+        if o is None:
+            return None
+        if self.is_torch:
+            if self.scalar:
+                return o.reshape(())
+            return o.reshape(tuple(reversed(self.pshape))).permute(*reversed(range(len(self.pshape))))
+        if self.missing is not None:
+            full = np.ma.masked_all(self.P, dtype=self.dtype)
+            full[~self.missing] = o
+            o = full
+        if self.scalar:
+            v = o.reshape(())[()]
+            return v if v is np.ma.masked else self.dtype.type(v)
+        return o.reshape(self.pshape, order="F")
+
+    def context(self, ctx):
+        ctx = ctx or get_context(self.device)
+        if self.is_torch:
+            import torch
+            ctx.set_stream(torch.cuda.current_stream(self.torch_device).cuda_stream)
+        else:
+            ctx.set_stream(None)
+        return ctx
+
+
+_SYMBOLS = ("rank", "bulk", "tail", "basic")
+# north-star symbol spellings -> reference estimators (SURVEY.md vocabulary map)
+_ESTIMATOR_ALIASES = {"mean": "mean", "median": "median", "std": "std", "squared": "std",
+                      "mad": "mad", "abs": "mad", "folded": "mad"}
+
+
+def _estimator(kind):
+    """Map an estimator `kind` to (code, p, p_is_f64) or None (src/ess_rhat.jl:628-659)."""
+    if isinstance(kind, Quantile):
+        p = kind.p
+        if isinstance(p, Fraction):
+            return "quantile", float(p), False
+        return "quantile", float(p), not isinstance(p, np.float32)
+    if isinstance(kind, str):
+        name = _ESTIMATOR_ALIASES.get(kind)
+        return (name, 0.0, False) if name else None
+    if kind is np.mean:
+        return "mean", 0.0, False
+    if kind is np.median:
+        return "median", 0.0, False
+    if kind is np.std:
+        return "std", 0.0, False
+    name = getattr(kind, "__name__", "")
+    if name == "median_abs_deviation":      # scipy.stats.median_abs_deviation ~ StatsBase.mad
+        return "mad", 0.0, False
+    tag = getattr(kind, "_mcd_estimator", None)
+    return (tag, 0.0, False) if tag in L.ESTIMATORS else None
+
+
+def _method_code(m):
+    if isinstance(m, type) and issubclass(m, AbstractAutocovMethod):
+        m = m()
+    if not isinstance(m, AbstractAutocovMethod) or m._code is None:
+        raise ArgumentError(f"autocov_method must be an AbstractAutocovMethod, got {m!r}")
+    return m._code
+
+
+def _tail_prob(tp):
+    if isinstance(tp, (Fraction, int)):
+        return float(Fraction(tp)), 0
+    return float(tp), (0 if isinstance(tp, np.float32) else 1)
+
+
+def _warn_niter(a: _Arr, split_chains: int):
+    niter = a.draws // split_chains
+    if not niter > 4:
+        warnings.warn(f"number of draws after splitting must be >4 but is {niter}. ESS cannot be computed.")
+
+
+def _check_split(split_chains):
+    if not isinstance(split_chains, (int, np.integer)) or split_chains < 1:
+        raise ArgumentError("split_chains must be a positive integer")
+
+
+def _call_ess_rhat(a, kind, want_ess, want_rhat, relative=False, autocov_method=None, split_chains=2,
+                   maxlag=250, tail_prob=Fraction(1, 10), ctx=None):
+    _check_split(split_chains)
+    ctx = a.context(ctx)
+    method = _method_code(autocov_method if autocov_method is not None else AutocovMethod())
+    if want_ess:
+        _warn_niter(a, split_chains)
+        if a.draws // split_chains > 4 and not maxlag > 0:
+            raise DomainError(f"maxlag must be >0. (got {maxlag})")
+    tp, tp64 = _tail_prob(tail_prob)
+    e = a.new_out() if want_ess else None
+    r = a.new_out() if want_rhat else None
+    rc = ctx._lib.mcd_ess_rhat(ctx._h, C.c_void_p(a.ptr), a.mem, a.code, a.draws, a.chains, a.nparams,
+                               L.KINDS[kind], method, int(split_chains), int(max(min(maxlag, 2**31 - 1), -1)),
+                               int(bool(relative)), tp, tp64, a.out_ptr(e), a.out_ptr(r))
+    ctx.check(rc, domain=True)
+    return a.finish(e), a.finish(r)
+
+
+def _call_estimator(a, est, relative=False, autocov_method=None, split_chains=2, maxlag=250, ctx=None,
+                    mcse_mode=False):
+    _check_split(split_chains)
+    name, p, p64 = est
+    ctx = a.context(ctx)
+    method = _method_code(autocov_method if autocov_method is not None else AutocovMethod())
+    _warn_niter(a, split_chains)
+    if a.draws // split_chains > 4 and not maxlag > 0:
+        raise DomainError(f"maxlag must be >0. (got {maxlag})")
+    out = a.new_out()
+    if mcse_mode:
+        rc = ctx._lib.mcd_mcse(ctx._h, C.c_void_p(a.ptr), a.mem, a.code, a.draws, a.chains, a.nparams,
+                               L.ESTIMATORS[name], p, int(p64), method, int(split_chains), int(maxlag),
+                               a.out_ptr(out))
+    else:
+        rc = ctx._lib.mcd_ess_estimator(ctx._h, C.c_void_p(a.ptr), a.mem, a.code, a.draws, a.chains, a.nparams,
+                                        L.ESTIMATORS[name], p, int(p64), method, int(split_chains), int(maxlag),
+                                        int(bool(relative)), a.out_ptr(out))
+    ctx.check(rc, domain=True)
+    return a.finish(out)
+
+
+# ---------------------------------------------------------------------------------------
+# public API
+# ---------------------------------------------------------------------------------------
+def ess(samples, *, kind="bulk", ctx=None, **kwargs):
+    """`ess(samples; kind=:bulk, relative=false, autocov_method=AutocovMethod(), split_chains=2,
+    maxlag=250, [tail_prob=1//10])`  (src/ess_rhat.jl:215-311)."""
+    a = _Arr(samples)
+    if isinstance(kind, str) and kind in ("bulk", "tail", "basic"):
+        if kind != "tail" and "tail_prob" in kwargs:
+            raise TypeError("ess() got an unexpected keyword argument 'tail_prob' for this kind")
+        return _call_ess_rhat(a, kind, True, False, ctx=ctx, **kwargs)[0]
+    if isinstance(kind, str) and kind == "rank":
+        raise ArgumentError(f"the `kind` `{kind}` is not supported by `ess`")
+    est = _estimator(kind)
+    if est is None:
+        if isinstance(kind, str):
+            raise ArgumentError(f"the `kind` `{kind}` is not supported by `ess`")
+        raise ArgumentError(f"the estimator {kind} is not yet supported by `ess`")
+    return _call_estimator(a, est, ctx=ctx, **kwargs)
+
+
+def rhat(samples, *, kind="rank", split_chains=2, ctx=None):
+    """`rhat(samples; kind=:rank, split_chains=2)`  (src/ess_rhat.jl:313-420)."""
+    if kind not in _SYMBOLS:
+        raise ArgumentError(f"the `kind` `{kind}` is not supported by `rhat`")
+    a = _Arr(samples)
+    return _call_ess_rhat(a, kind, False, True, split_chains=split_chains, ctx=ctx)[1]
+
+
+def ess_rhat(samples, *, kind="rank", ctx=None, **kwargs):
+    """`ess_rhat(samples; kind=:rank, kwargs...) -> (; ess, rhat)`  (src/ess_rhat.jl:422-455)."""
+    if kind not in _SYMBOLS:
+        raise ArgumentError(f"the `kind` `{kind}` is not supported by `ess_rhat`")
+    a = _Arr(samples)
+    if kind != "tail" and "tail_prob" in kwargs:
+        raise TypeError("ess_rhat() got an unexpected keyword argument 'tail_prob' for this kind")
+    e, r = _call_ess_rhat(a, kind, True, True, ctx=ctx, **kwargs)
+    return ESSRhat(e, r)
+
+
+def mcse(samples, *, kind=np.mean, ctx=None, **kwargs):
+    """`mcse(samples; kind=Statistics.mean, kwargs...)`  (src/mcse.jl:5-42).
+
+    mean / std / median / quantile use the ESS-based rules on the GPU.  Any other estimator
+    uses the reference's subsampling-bootstrap fallback (src/mcse.jl:120-148), which calls a
+    user closure per window and therefore stays on the host (out of scope)."""
+    est = _estimator(kind)
+    if est is None or est[0] == "mad":
+        raise NotImplementedError(
+            "mcse for this estimator uses the subsampling bootstrap (SBM) of the reference, "
+            "which stays in the host language and is outside the accelerated path")
+    a = _Arr(samples)
+    kwargs.pop("relative", None)
+    return _call_estimator(a, est, ctx=ctx, mcse_mode=True, **kwargs)
+
+
+def _validate_superchain_ids(superchain_ids, nchains):
+    """`_validate_superchain_ids` + `unique_indices` (src/rhat_nested.jl:68-81, src/utils.jl:50-64):
+    superchains ordered by sorted label, chains within a superchain by first appearance.
+    Returns a 0-based int32 matrix (chains_per_super x nsuper), column-major."""
+    ids = list(superchain_ids)
+    if len(ids) != nchains:
+        raise DimensionMismatch(
+            f"`superchain_ids` has length {len(ids)} but `samples` has {nchains} chains")
+    groups: dict = {}
+    for i, s in enumerate(ids):
+        groups.setdefault(s, []).append(i)
+    keys = sorted(groups)
+    if len(keys) < 2:
+        raise ArgumentError(f"at least 2 superchains are required, got {len(keys)}")
+    if len({len(groups[k]) for k in keys}) != 1:
+        raise ArgumentError("all superchains must contain the same number of chains")
+    return np.asfortranarray(np.stack([np.asarray(groups[k], dtype=np.int32) for k in keys], axis=1))
+
+
+def rhat_nested(samples, superchain_ids, *, kind="rank", split_chains=2, ctx=None):
+    """`rhat_nested(samples, superchain_ids; kind=:rank, split_chains=2)`  (src/rhat_nested.jl:1-66)."""
+    ndim = samples.ndim if hasattr(samples, "ndim") else np.asarray(samples).ndim
+    if ndim < 2:
+        raise ArgumentError("`samples` must have at least 2 dimensions `(draws, chains[, parameters…])`")
+    a = _Arr(samples)
+    inds = _validate_superchain_ids(superchain_ids, a.chains)
+    if kind not in _SYMBOLS:
+        raise ArgumentError(f"the `kind` `{kind}` is not supported by `rhat_nested`")
+    _check_split(split_chains)
+    ctx = a.context(ctx)
+    out = a.new_out()
+    rc = ctx._lib.mcd_rhat_nested(ctx._h, C.c_void_p(a.ptr), a.mem, a.code, a.draws, a.chains, a.nparams,
+                                  C.c_void_p(inds.ctypes.data), inds.shape[0], inds.shape[1], L.KINDS[kind],
+                                  int(split_chains), a.out_ptr(out))
+    ctx.check(rc)
+    return a.finish(out)
+
+
+# ---------------------------------------------------------------------------------------
+# transforms (exposed for parity checks) and the synthetic generator
+# ---------------------------------------------------------------------------------------
+def _transform(samples, fn_name, out_dtype, ctx=None):
+    a = _Arr(samples)
+    if a.missing is not None:
+        raise ArgumentError("masked input is not supported by the transform helpers")
+    ctx = a.context(ctx)
+    shape3 = (a.draws, a.chains, a.nparams)
+    if a.is_torch:
+        import torch
+        tdt = torch.float64 if out_dtype == np.float64 else torch.float32
+        out = torch.empty((a.nparams, a.chains, a.draws), dtype=tdt, device=a.torch_device)
+        ptr = C.c_void_p(out.data_ptr())
+    else:
+        out = np.empty(shape3, dtype=out_dtype, order="F")
+        ptr = C.c_void_p(out.ctypes.data)
+    rc = getattr(ctx._lib, fn_name)(ctx._h, C.c_void_p(a.ptr), a.mem, a.code, a.draws, a.chains, a.nparams, ptr)
+    ctx.check(rc)
+    if a.is_torch:
+        out = out.permute(2, 1, 0)
+        return out.reshape((a.draws, a.chains) + a.pshape) if len(a.pshape) != 1 else out
+    full_shape = (a.draws,) + ((a.chains,) if np.ndim(samples) > 1 else ()) + a.pshape
+    return out.reshape(full_shape, order="F")
+
+
+def tiedrank(samples, ctx=None):
+    """StatsBase.tiedrank of every parameter's flattened draws x chains slab, as Float64."""
+    return _transform(samples, "mcd_tiedrank", np.float64, ctx)
+
+
+def rank_normalize(samples, ctx=None):
+    """`_rank_normalize` (src/utils.jl:169-193)."""
+    a_dt = np.float32 if getattr(samples, "dtype", None) in (np.float32,) or str(getattr(samples, "dtype", "")) == "torch.float32" else np.float64
+    return _transform(samples, "mcd_rank_normalize", a_dt, ctx)
+
+
+def fold_around_median(samples, ctx=None):
+    """`_fold_around_median` (src/utils.jl:148-158)."""
+    a_dt = np.float32 if getattr(samples, "dtype", None) in (np.float32,) or str(getattr(samples, "dtype", "")) == "torch.float32" else np.float64
+    return _transform(samples, "mcd_fold_around_median", a_dt, ctx)
+
+
+def generate_ar1(phi, sigma, draws, chains, params, *, dtype="float64", seed=1, param_offset=0, device=0, ctx=None):
+    """AR(1) chains as test/helpers.jl:4-12, generated on the GPU; returns a CUDA torch tensor of
+    logical shape (draws, chains, params) in column-major layout."""
+    import torch
+    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    dev = torch.device("cuda", device)
+    buf = torch.empty((params, chains, draws), dtype=tdt, device=dev)
+    ctx = ctx or get_context(device)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    rc = ctx._lib.mcd_generate_ar1(ctx._h, L.MCD_F64 if tdt == torch.float64 else L.MCD_F32, draws, chains,
+                                   params, int(param_offset), float(phi), float(sigma), int(seed),
+                                   C.c_void_p(buf.data_ptr()))
+    ctx.check(rc)
+    return buf.permute(2, 1, 0)

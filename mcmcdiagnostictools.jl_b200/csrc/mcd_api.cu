@@ -1,0 +1,751 @@
+// mcd_api.cu — C ABI of libmcmcdiag_b200.so (see include/mcmcdiag_b200.h).
+// Context, program construction (which transform / reduce steps a reference call maps
+// to), path selection (shared-memory slab kernel vs global-memory large-slab pipeline),
+// host staging pipeline, lookup tables and the AR(1) generator.
+#include "../../include/mcmcdiag_b200.h"
+#include "mcd_common.cuh"
+#include "mcd_slab.cuh"
+#include "mcd_large.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace mcd;
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+struct mcd_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  std::mutex mu;
+  std::string err;
+  int sm_count = 0;
+  int smem_optin = 0;
+  // cached tables
+  void* ztab = nullptr; long long ztab_n = 0; int ztab_dtype = -1; size_t ztab_cap = 0;
+  void* tw = nullptr; int tw_n = 0; int tw_dtype = -1; size_t tw_cap = 0;
+  unsigned* d_flags = nullptr;
+  int* d_chain_inds = nullptr; size_t chain_inds_cap = 0;
+  // staging / workspace
+  void* stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0};
+  void* d_out[2] = {nullptr, nullptr}; size_t out_cap[2] = {0, 0};
+  void* d_arr = nullptr; size_t arr_cap = 0;
+  void* work = nullptr; size_t work_cap = 0;
+  // options
+  int force_path = 0;
+  long long h2d_chunk_bytes = 256ll << 20;
+  long long workspace_bytes = 6ll << 30;
+  int bucket_limit = 64;
+  // stats
+  long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  int last_path = 0;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(mcd_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? MCD_ENOMEM : MCD_ECUDA, "%s failed: %s", \
+                  #call, cudaGetErrorString(e_));                                             \
+  } while (0)
+
+static int ensure_cap(mcd_ctx* ctx, void** p, size_t* cap, size_t need) {
+  if (*cap >= need && *p) return MCD_OK;
+  if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+  if (need == 0) need = 256;
+  CU(cudaMalloc(p, need));
+  *cap = need;
+  return MCD_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// small kernels: tables and the generator
+// ---------------------------------------------------------------------------------------
+template <typename T> __global__ void ztab_kernel(T* ztab, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < 2 * n - 1) ztab[i] = z_from_rank2<T>(i + 2, n);
+}
+
+template <typename T> __global__ void twiddle_kernel(Cx<T>* tw, int N) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < N) {
+    double s, c;
+    sincospi(-2.0 * (double)k / (double)N, &s, &c);
+    Cx<T> w; w.x = (T)c; w.y = (T)s;
+    tw[k] = w;
+  }
+}
+
+// Philox4x32-10 counter-based generator (Salmon et al., SC'11).
+__device__ __forceinline__ void philox4x32_10(unsigned c[4], unsigned k0, unsigned k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    unsigned n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+// One thread per (chain, param) series: test/helpers.jl:4-12.  Draw pairs (2i, 2i+1) come
+// from one Philox block keyed by seed with counter (i, chain, param_lo, param_hi).
+template <typename T>
+__global__ void ar1_kernel(T* x, long long draws, long long chains, long long params,
+                           long long param_offset, double phi, double sigma, unsigned long long seed) {
+  long long sid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (sid >= chains * params) return;
+  long long param = sid / chains, chain = sid % chains;
+  unsigned long long gp = (unsigned long long)(param + param_offset);
+  T* dst = x + sid * draws;
+  double prev = 0.0;
+  for (long long t0 = 0; t0 < draws; t0 += 2) {
+    unsigned c[4] = {(unsigned)(t0 >> 1), (unsigned)chain, (unsigned)gp, (unsigned)(gp >> 32)};
+    philox4x32_10(c, (unsigned)seed, (unsigned)(seed >> 32));
+    // two uniforms in (0,1) from 64 bits each
+    const double u1 = ((double)c[0] * 4294967296.0 + (double)c[1] + 0.5) * 5.421010862427522e-20;
+    const double u2 = ((double)c[2] * 4294967296.0 + (double)c[3] + 0.5) * 5.421010862427522e-20;
+    double r = sqrt(-2.0 * log(u1));
+    double s, co;
+    sincospi(2.0 * u2, &s, &co);
+    double e0 = r * co, e1 = r * s;
+    double v0 = (t0 == 0) ? sigma * e0 : fma(phi, prev, sigma * e0);
+    dst[t0] = (T)v0;
+    prev = (double)(T)v0;
+    if (t0 + 1 < draws) {
+      double v1 = fma(phi, prev, sigma * e1);
+      dst[t0 + 1] = (T)v1;
+      prev = (double)(T)v1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// program = what one reference call asks for
+// ---------------------------------------------------------------------------------------
+struct Program {
+  int nsteps = 0;
+  Step steps[MAX_STEPS];
+  int combine = CB_PLAIN;
+  int method = 0, maxlag = 1, relative = 0, ess_nan = 0;
+  double mcse_p = 0.5;
+  bool want_ess = false, want_rhat = false, want_arr = false;
+  int arr_elem_bytes = 0;  // element size of arr_out (0 = none)
+  const int32_t* chain_inds = nullptr; long long cps = 0, nsuper = 0;
+  void add(int tr, int rd, double p = 0.0, int p_f32 = 0) {
+    steps[nsteps].transform = tr; steps[nsteps].reduce = rd; steps[nsteps].p = p; steps[nsteps].p_f32 = p_f32;
+    ++nsteps;
+  }
+};
+
+static int next_pow2(long long v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+static long long nextprod23(long long n) {
+  long long best = -1;
+  for (long long p3 = 1;; p3 *= 3) {
+    long long v = p3;
+    while (v < n) v *= 2;
+    if (best < 0 || v < best) best = v;
+    if (p3 >= n) break;
+  }
+  return best;
+}
+
+static int ensure_ztab(mcd_ctx* ctx, int dtype, long long n) {
+  if (ctx->ztab && ctx->ztab_n == n && ctx->ztab_dtype == dtype) return MCD_OK;
+  size_t ts = dtype == MCD_F64 ? 8 : 4;
+  int rc = ensure_cap(ctx, &ctx->ztab, &ctx->ztab_cap, (size_t)(2 * n - 1) * ts);
+  if (rc) return rc;
+  long long cnt = 2 * n - 1;
+  int blocks = (int)((cnt + 255) / 256);
+  if (dtype == MCD_F64) ztab_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double*)ctx->ztab, n);
+  else ztab_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float*)ctx->ztab, n);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  ctx->ztab_n = n; ctx->ztab_dtype = dtype;
+  return MCD_OK;
+}
+
+static int ensure_twiddle(mcd_ctx* ctx, int dtype, int N) {
+  if (ctx->tw && ctx->tw_n == N && ctx->tw_dtype == dtype) return MCD_OK;
+  size_t ts = dtype == MCD_F64 ? 16 : 8;
+  int rc = ensure_cap(ctx, &ctx->tw, &ctx->tw_cap, (size_t)N * ts);
+  if (rc) return rc;
+  int blocks = (N + 255) / 256;
+  if (dtype == MCD_F64) twiddle_kernel<double><<<blocks, 256, 0, ctx->stream>>>((Cx<double>*)ctx->tw, N);
+  else twiddle_kernel<float><<<blocks, 256, 0, ctx->stream>>>((Cx<float>*)ctx->tw, N);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  ctx->tw_n = N; ctx->tw_dtype = dtype;
+  return MCD_OK;
+}
+
+static bool program_needs_ranks(const Program& pg) {
+  for (int s = 0; s < pg.nsteps; ++s) {
+    int t = pg.steps[s].transform;
+    if (t == TR_RANKNORM || t == TR_FOLD_RANKNORM) return true;
+  }
+  return false;
+}
+
+constexpr int SLAB_THREADS = 256;
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Lay the slab kernel's shared memory out; returns total bytes.
+template <typename T>
+static size_t slab_layout(SlabArgs<T>& a, const Program& pg) {
+  const size_t ts = sizeof(T);
+  const int n = a.g.n;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (int)o; };
+  a.offX = take((size_t)n * ts);
+  a.offY = take((size_t)n * ts);
+  a.offK = take((size_t)n * ts);
+  a.offCNT = take((size_t)a.nbuckets * 4);
+  size_t view_bytes = off - (size_t)a.offK;
+  a.offCM = take((size_t)a.g.nch * ts);
+  a.offCV = take((size_t)a.g.nch * ts);
+  a.offGAM = take((size_t)(a.maxlag + 1 + LAG_BATCH) * ts);
+  a.offGSUM = take(pg.method == MCD_AUTOCOV_FFT ? (size_t)(a.maxlag + 1) * 8 : 0);
+  size_t part = (size_t)(SLAB_THREADS / 32) * LAG_BATCH;
+  if ((size_t)(2 * pg.nsuper) > part) part = (size_t)(2 * pg.nsuper);
+  a.offPART = take(part * 8);
+  a.offFFT = a.offK;
+  if (pg.method == MCD_AUTOCOV_FFT && pg.want_ess) {
+    size_t need = (size_t)a.fft_n * 2 * 2 * ts;
+    if (need > view_bytes) a.offFFT = take(need);
+  }
+  a.offMISC = take(sizeof(Misc));
+  return off;
+}
+
+template <typename T>
+static int run_slab(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom& g, const Program& pg,
+                    T* d_ess, T* d_rhat, void* d_arr, bool* handled) {
+  *handled = false;
+  SlabArgs<T> a;
+  memset(&a, 0, sizeof a);
+  a.x = dx; a.params = params; a.g = g;
+  a.nsteps = pg.nsteps;
+  for (int s = 0; s < pg.nsteps; ++s) a.steps[s] = pg.steps[s];
+  a.combine = pg.combine; a.method = pg.method; a.maxlag = pg.maxlag; a.relative = pg.relative;
+  a.ess_nan = pg.ess_nan;
+  const long long ntotal = (long long)g.niter * g.nch;
+  if (sizeof(T) == 8) a.rel_ess_max = (T)log10((double)ntotal);
+  else a.rel_ess_max = (T)log10f((float)ntotal);
+  a.ess_out = d_ess; a.rhat_out = d_rhat; a.arr_out = d_arr;
+  a.nbuckets = std::min(std::max(next_pow2(g.n), SLAB_THREADS), 16384);
+  a.bucket_limit = ctx->bucket_limit;
+  a.fft_n = (pg.method == MCD_AUTOCOV_FFT && pg.want_ess && !pg.ess_nan) ? (int)nextprod23(2ll * g.niter - 1) : 0;
+  a.cps = (int)pg.cps; a.nsuper = (int)pg.nsuper;
+  a.mcse_p = pg.mcse_p;
+  a.flags = ctx->d_flags;
+  if (g.nch > 4096 || pg.nsuper > 4096) return MCD_OK;
+  const size_t smem = slab_layout<T>(a, pg);
+  if (smem > (size_t)ctx->smem_optin) return MCD_OK;  // not handled: caller uses the large path
+
+  const int dtype = sizeof(T) == 8 ? MCD_F64 : MCD_F32;
+  if (program_needs_ranks(pg)) {
+    int rc = ensure_ztab(ctx, dtype, g.n);
+    if (rc) return rc;
+    a.ztab = (const T*)ctx->ztab;
+  }
+  if (a.fft_n) {
+    int rc = ensure_twiddle(ctx, dtype, a.fft_n);
+    if (rc) return rc;
+    a.twiddle = ctx->tw;
+  }
+  if (pg.chain_inds) a.chain_inds = ctx->d_chain_inds;
+
+  auto kern = slab_kernel<T, SLAB_THREADS>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long grid = std::min<long long>(params, 1ll << 30);
+  if (grid > 0) {
+    kern<<<(unsigned)grid, SLAB_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  ctx->last_path = 1;
+  *handled = true;
+  return MCD_OK;
+}
+
+// Run a program on device-resident data (params slabs).  Outputs are device pointers.
+template <typename T>
+static int run_device(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom& g, const Program& pg,
+                      T* d_ess, T* d_rhat, void* d_arr) {
+  if (params == 0) return MCD_OK;
+  bool handled = false;
+  if (ctx->force_path != 2) {
+    int rc = run_slab<T>(ctx, dx, params, g, pg, d_ess, d_rhat, d_arr, &handled);
+    if (rc) return rc;
+    if (handled) return MCD_OK;
+    if (ctx->force_path == 1)
+      return fail(ctx, MCD_EUNSUPPORTED, "slab of %d values does not fit the shared-memory kernel", g.n);
+  }
+  LargeEnv env;
+  env.stream = ctx->stream; env.sm_count = ctx->sm_count; env.flags = ctx->d_flags;
+  env.workspace_bytes = ctx->workspace_bytes; env.launches = &ctx->launches;
+  env.work = &ctx->work; env.work_cap = &ctx->work_cap; env.smem_optin = ctx->smem_optin;
+  env.d_chain_inds = ctx->d_chain_inds;
+  std::string msg;
+  int rc = run_large<T>(env, dx, params, g, pg.nsteps, pg.steps, pg.combine, pg.method, pg.maxlag, pg.relative,
+                        pg.ess_nan, pg.mcse_p, (int)pg.cps, (int)pg.nsuper, d_ess, d_rhat, d_arr, msg);
+  if (rc) return fail(ctx, rc, "%s", msg.c_str());
+  ctx->last_path = 2;
+  return MCD_OK;
+}
+
+static int read_flags(mcd_ctx* ctx, unsigned* out) {
+  CU(cudaMemcpyAsync(out, ctx->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MCD_OK;
+}
+
+// Common driver: handles host staging (chunked, double-buffered, overlapped) or the
+// device-resident fast path, then surfaces kernel-raised flags.
+template <typename T>
+static int execute_t(mcd_ctx* ctx, const void* x, int mem, long long draws, long long chains, long long params,
+                     int split, Program& pg, void* ess_out, void* rhat_out, void* arr_out) {
+  if (draws <= 0 || chains <= 0 || params < 0) return fail(ctx, MCD_EINVAL, "draws and chains must be positive");
+  if (split < 1) return fail(ctx, MCD_EINVAL, "split_chains must be >= 1");
+  if (draws * chains > (1ll << 30)) return fail(ctx, MCD_EUNSUPPORTED, "slab too large (draws*chains > 2^30)");
+  if (params > 0 && !x) return fail(ctx, MCD_EINVAL, "x is NULL");
+  SplitGeom g((int)draws, (int)chains, split);
+  const long long n = g.n;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemsetAsync(ctx->d_flags, 0, sizeof(unsigned), ctx->stream));
+  if (pg.chain_inds) {
+    size_t bytes = (size_t)(pg.cps * pg.nsuper) * sizeof(int);
+    int rc = ensure_cap(ctx, (void**)&ctx->d_chain_inds, &ctx->chain_inds_cap, bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->d_chain_inds, pg.chain_inds, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (mem == MCD_DEVICE) {
+    int rc = run_device<T>(ctx, (const T*)x, params, g, pg, (T*)ess_out, (T*)rhat_out, arr_out);
+    if (rc) return rc;
+    // flags are only consulted for programs that can raise an error
+    bool can_raise = false;
+    for (int s = 0; s < pg.nsteps; ++s) can_raise |= (pg.steps[s].transform == TR_IND_QUANTILE);
+    if (can_raise) {
+      unsigned fl = 0;
+      rc = read_flags(ctx, &fl);
+      if (rc) return rc;
+      if (fl & FLAG_NAN_QUANTILE) return fail(ctx, MCD_ENAN, "quantiles are undefined in presence of NaNs");
+    }
+    return MCD_OK;
+  }
+  if (mem != MCD_HOST) return fail(ctx, MCD_EINVAL, "bad mem kind %d", mem);
+
+  // ---- host-resident input: chunk the parameter axis, overlap H2D with compute ------------
+  const size_t slab_bytes = (size_t)n * sizeof(T);
+  long long chunk = std::max<long long>(1, ctx->h2d_chunk_bytes / (long long)slab_bytes);
+  chunk = std::min(chunk, std::max<long long>(params, 1));
+  int rc = MCD_OK;
+  for (int i = 0; i < 2; ++i) {
+    rc = ensure_cap(ctx, &ctx->stage[i], &ctx->stage_cap[i], (size_t)chunk * slab_bytes);
+    if (rc) return rc;
+    rc = ensure_cap(ctx, &ctx->d_out[i], &ctx->out_cap[i], (size_t)std::max<long long>(params, 1) * sizeof(T));
+    if (rc) return rc;
+  }
+  if (pg.want_arr) {
+    rc = ensure_cap(ctx, &ctx->d_arr, &ctx->arr_cap, (size_t)chunk * n * pg.arr_elem_bytes);
+    if (rc) return rc;
+  }
+  T* d_ess = pg.want_ess ? (T*)ctx->d_out[0] : nullptr;
+  T* d_rhat = pg.want_rhat ? (T*)ctx->d_out[1] : nullptr;
+  long long done = 0;
+  int it = 0;
+  while (done < params) {
+    const long long cnt = std::min(chunk, params - done);
+    const int b = it & 1;
+    if (it >= 2) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+    CU(cudaMemcpyAsync(ctx->stage[b], (const char*)x + (size_t)done * slab_bytes, (size_t)cnt * slab_bytes,
+                       cudaMemcpyHostToDevice, ctx->copy_stream));
+    ctx->h2d_bytes += cnt * (long long)slab_bytes;
+    CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+    rc = run_device<T>(ctx, (const T*)ctx->stage[b], cnt, g, pg, d_ess ? d_ess + done : nullptr,
+                       d_rhat ? d_rhat + done : nullptr, pg.want_arr ? ctx->d_arr : nullptr);
+    if (rc) return rc;
+    if (pg.want_arr) {
+      size_t bytes = (size_t)cnt * n * pg.arr_elem_bytes;
+      CU(cudaMemcpyAsync((char*)arr_out + (size_t)done * n * pg.arr_elem_bytes, ctx->d_arr, bytes,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->d2h_bytes += (long long)bytes;
+    }
+    CU(cudaEventRecord(ctx->ev_done[b], ctx->stream));
+    done += cnt;
+    ++it;
+  }
+  if (d_ess && ess_out) {
+    CU(cudaMemcpyAsync(ess_out, d_ess, (size_t)params * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->d2h_bytes += params * (long long)sizeof(T);
+  }
+  if (d_rhat && rhat_out) {
+    CU(cudaMemcpyAsync(rhat_out, d_rhat, (size_t)params * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->d2h_bytes += params * (long long)sizeof(T);
+  }
+  unsigned fl = 0;
+  rc = read_flags(ctx, &fl);  // also synchronises the stream
+  if (rc) return rc;
+  if (fl & FLAG_NAN_QUANTILE) return fail(ctx, MCD_ENAN, "quantiles are undefined in presence of NaNs");
+  return MCD_OK;
+}
+
+static int execute(mcd_ctx* ctx, const void* x, int mem, int dtype, long long draws, long long chains,
+                   long long params, int split, Program& pg, void* ess_out, void* rhat_out, void* arr_out) {
+  if (dtype == MCD_F64) return execute_t<double>(ctx, x, mem, draws, chains, params, split, pg, ess_out, rhat_out, arr_out);
+  if (dtype == MCD_F32) return execute_t<float>(ctx, x, mem, draws, chains, params, split, pg, ess_out, rhat_out, arr_out);
+  return fail(ctx, MCD_EINVAL, "bad dtype %d", dtype);
+}
+
+// maxlag / niter rules of _ess_rhat(Val(:basic)) (src/ess_rhat.jl:469-484)
+static int setup_ess(mcd_ctx* ctx, Program& pg, long long draws, int split, int method, int maxlag, int relative) {
+  if (method < 0 || method > 2) return fail(ctx, MCD_EINVAL, "unknown autocov_method %d", method);
+  if (split < 1) return fail(ctx, MCD_EINVAL, "split_chains must be >= 1");
+  const long long niter = draws / split;
+  pg.method = method; pg.relative = relative ? 1 : 0;
+  if (!(niter > 4)) { pg.ess_nan = 1; pg.maxlag = 1; return MCD_OK; }
+  if (!(maxlag > 0)) return fail(ctx, MCD_EINVAL, "maxlag must be >0.");
+  pg.maxlag = (int)std::min<long long>(maxlag, niter - 4);
+  return MCD_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int mcd_abi_version(void) { return MCD_ABI_VERSION; }
+const char* mcd_create_error(void) { return g_create_err.c_str(); }
+
+int mcd_create(mcd_ctx** out, int device) {
+  if (!out) return MCD_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, MCD_ECUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, MCD_EINVAL, "device %d out of range [0,%d)", device, ndev);
+  mcd_ctx* ctx = new (std::nothrow) mcd_ctx();
+  if (!ctx) return MCD_ENOMEM;
+  ctx->device = device;
+  auto bail = [&](const char* what, cudaError_t er) {
+    fail(nullptr, MCD_ECUDA, "%s: %s", what, cudaGetErrorString(er));
+    delete ctx;
+    return MCD_ECUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  if (prop.major < 10) {
+    fail(nullptr, MCD_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+         prop.major, prop.minor);
+    delete ctx;
+    return MCD_ECUDA;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  ctx->stream = ctx->own_stream;
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+  }
+  if ((e = cudaMalloc(&ctx->d_flags, sizeof(unsigned))) != cudaSuccess) return bail("cudaMalloc", e);
+  *out = ctx;
+  return MCD_OK;
+}
+
+void mcd_destroy(mcd_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  void* ptrs[] = {ctx->ztab, ctx->tw, ctx->d_flags, ctx->d_chain_inds, ctx->stage[0], ctx->stage[1],
+                  ctx->d_out[0], ctx->d_out[1], ctx->d_arr, ctx->work};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+const char* mcd_last_error(const mcd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int mcd_set_stream(mcd_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return MCD_OK;
+}
+
+int mcd_synchronize(mcd_ctx* ctx) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->copy_stream));
+  return MCD_OK;
+}
+
+int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
+  if (!ctx || !key) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::string k(key);
+  if (k == "force_path") { if (value < 0 || value > 2) return fail(ctx, MCD_EINVAL, "force_path in 0..2"); ctx->force_path = (int)value; }
+  else if (k == "h2d_chunk_bytes") { if (value < 1) return fail(ctx, MCD_EINVAL, "h2d_chunk_bytes >= 1"); ctx->h2d_chunk_bytes = value; }
+  else if (k == "workspace_bytes") { if (value < (1 << 20)) return fail(ctx, MCD_EINVAL, "workspace_bytes >= 1 MiB"); ctx->workspace_bytes = value; }
+  else if (k == "sort_bucket_limit") { if (value < 0) return fail(ctx, MCD_EINVAL, "sort_bucket_limit >= 0"); ctx->bucket_limit = (int)value; }
+  else return fail(ctx, MCD_EINVAL, "unknown option '%s'", key);
+  return MCD_OK;
+}
+
+int64_t mcd_get_stat(const mcd_ctx* ctx, const char* key) {
+  if (!ctx || !key) return -1;
+  std::string k(key);
+  if (k == "kernel_launches") return ctx->launches;
+  if (k == "last_path") return ctx->last_path;
+  if (k == "h2d_bytes") return ctx->h2d_bytes;
+  if (k == "d2h_bytes") return ctx->d2h_bytes;
+  if (k == "sm_count") return ctx->sm_count;
+  if (k == "smem_optin") return ctx->smem_optin;
+  return -1;
+}
+
+int mcd_ess_rhat(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,
+                 int kind, int autocov_method, int split_chains, int maxlag, int relative, double tail_prob,
+                 int tail_prob_f64, void* ess_out, void* rhat_out) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->err.clear();
+  if (!ess_out && !rhat_out) return fail(ctx, MCD_EINVAL, "both outputs are NULL");
+  if (kind < 0 || kind > 3) return fail(ctx, MCD_EINVAL, "the `kind` %d is not supported", kind);
+  Program pg;
+  pg.want_ess = ess_out != nullptr; pg.want_rhat = rhat_out != nullptr;
+  if (pg.want_ess) { int rc = setup_ess(ctx, pg, draws, split_chains, autocov_method, maxlag, relative); if (rc) return rc; }
+  const int rd = pg.want_ess ? RD_ESS_RHAT : RD_RHAT;
+  const int p_f32 = (dtype == MCD_F32 && !tail_prob_f64) ? 1 : 0;
+  double pl, pu;
+  if (p_f32) { pl = (double)(float)(tail_prob / 2); pu = (double)(float)(1.0 - tail_prob / 2); }
+  else { pl = tail_prob / 2; pu = 1.0 - tail_prob / 2; }
+  switch (kind) {
+    case MCD_KIND_BASIC: pg.add(TR_NONE, rd); break;
+    case MCD_KIND_BULK: pg.add(TR_RANKNORM, rd); break;
+    case MCD_KIND_TAIL:
+      if (pg.want_ess) {
+        if (!(pl >= 0.0 && pl <= 1.0 && pu >= 0.0 && pu <= 1.0)) return fail(ctx, MCD_EINVAL, "tail_prob out of range");
+        pg.add(TR_IND_QUANTILE, RD_ESS_RHAT, pl, p_f32);
+        pg.add(TR_IND_QUANTILE, RD_ESS_RHAT, pu, p_f32);
+        if (pg.want_rhat) { pg.add(TR_FOLD_RANKNORM, RD_RHAT); pg.combine = CB_TAIL; }
+        else pg.combine = CB_TAIL_ESS;
+      } else pg.add(TR_FOLD_RANKNORM, RD_RHAT);
+      break;
+    case MCD_KIND_RANK:
+      if (!pg.want_rhat) return fail(ctx, MCD_EINVAL, "the `kind` `rank` is not supported by `ess`");
+      pg.add(TR_RANKNORM, rd);
+      pg.add(TR_FOLD_RANKNORM, RD_RHAT);
+      pg.combine = CB_RANK;
+      break;
+  }
+  return execute(ctx, x, mem, dtype, draws, chains, params, split_chains, pg, ess_out, rhat_out, nullptr);
+}
+
+static int estimator_step(mcd_ctx* ctx, Program& pg, int estimator, double p, int p_f32) {
+  switch (estimator) {
+    case MCD_EST_MEAN: pg.add(TR_NONE, RD_ESS_RHAT); break;
+    case MCD_EST_MEDIAN: pg.add(TR_IND_MEDIAN, RD_ESS_RHAT); break;
+    case MCD_EST_STD: pg.add(TR_STDPROXY, RD_ESS_RHAT); break;
+    case MCD_EST_MAD: pg.add(TR_FOLD_IND_MEDIAN, RD_ESS_RHAT); break;
+    case MCD_EST_QUANTILE:
+      if (!(p >= 0.0 && p <= 1.0)) return fail(ctx, MCD_EINVAL, "input probability out of [0,1] range");
+      pg.add(TR_IND_QUANTILE, RD_ESS_RHAT, p, p_f32);
+      break;
+    default: return fail(ctx, MCD_EINVAL, "the estimator %d is not yet supported by `ess`", estimator);
+  }
+  return MCD_OK;
+}
+
+int mcd_ess_estimator(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains,
+                      int64_t params, int estimator, double p, int p_f64, int autocov_method, int split_chains,
+                      int maxlag, int relative, void* ess_out) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->err.clear();
+  if (!ess_out) return fail(ctx, MCD_EINVAL, "ess_out is NULL");
+  Program pg;
+  pg.want_ess = true;
+  int rc = setup_ess(ctx, pg, draws, split_chains, autocov_method, maxlag, relative);
+  if (rc) return rc;
+  const int p_f32 = (dtype == MCD_F32 && !p_f64) ? 1 : 0;
+  rc = estimator_step(ctx, pg, estimator, p_f32 ? (double)(float)p : p, p_f32);
+  if (rc) return rc;
+  return execute(ctx, x, mem, dtype, draws, chains, params, split_chains, pg, ess_out, nullptr, nullptr);
+}
+
+int mcd_mcse(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,
+             int estimator, double p, int p_f64, int autocov_method, int split_chains, int maxlag, void* mcse_out) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->err.clear();
+  if (!mcse_out) return fail(ctx, MCD_EINVAL, "mcse_out is NULL");
+  Program pg;
+  pg.want_ess = true;
+  int rc = setup_ess(ctx, pg, draws, split_chains, autocov_method, maxlag, 0);
+  if (rc) return rc;
+  const int p_f32 = (dtype == MCD_F32 && !p_f64) ? 1 : 0;
+  switch (estimator) {
+    case MCD_EST_MEAN: pg.combine = CB_MCSE_MEAN; break;
+    case MCD_EST_STD: pg.combine = CB_MCSE_STD; break;
+    case MCD_EST_MEDIAN: pg.combine = CB_MCSE_QUANTILE; pg.mcse_p = 0.5; break;
+    case MCD_EST_QUANTILE: pg.combine = CB_MCSE_QUANTILE; pg.mcse_p = p; break;
+    default:
+      return fail(ctx, MCD_EUNSUPPORTED, "mcse for estimator %d uses the subsampling bootstrap, which stays in the host language", estimator);
+  }
+  rc = estimator_step(ctx, pg, estimator, p_f32 ? (double)(float)p : p, p_f32);
+  if (rc) return rc;
+  return execute(ctx, x, mem, dtype, draws, chains, params, split_chains, pg, mcse_out, nullptr, nullptr);
+}
+
+int mcd_rhat_nested(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,
+                    const int32_t* chain_inds, int64_t chains_per_super, int64_t nsuper, int kind, int split_chains,
+                    void* rhat_out) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->err.clear();
+  if (!rhat_out || !chain_inds) return fail(ctx, MCD_EINVAL, "NULL argument");
+  if (nsuper < 2) return fail(ctx, MCD_EINVAL, "at least 2 superchains are required, got %lld", (long long)nsuper);
+  if (chains_per_super < 1 || chains_per_super * nsuper > chains)
+    return fail(ctx, MCD_EINVAL, "chain_inds shape (%lld x %lld) does not match %lld chains", (long long)chains_per_super,
+                (long long)nsuper, (long long)chains);
+  for (int64_t i = 0; i < chains_per_super * nsuper; ++i)
+    if (chain_inds[i] < 0 || chain_inds[i] >= chains) return fail(ctx, MCD_EINVAL, "chain index %d out of range", chain_inds[i]);
+  if (kind < 0 || kind > 3) return fail(ctx, MCD_EINVAL, "the `kind` %d is not supported by `rhat_nested`", kind);
+  Program pg;
+  pg.want_rhat = true;
+  pg.chain_inds = chain_inds; pg.cps = chains_per_super; pg.nsuper = nsuper;
+  switch (kind) {
+    case MCD_KIND_BASIC: pg.add(TR_NONE, RD_NESTED); break;
+    case MCD_KIND_BULK: pg.add(TR_RANKNORM, RD_NESTED); break;
+    case MCD_KIND_TAIL: pg.add(TR_FOLD_RANKNORM, RD_NESTED); break;
+    case MCD_KIND_RANK: pg.add(TR_RANKNORM, RD_NESTED); pg.add(TR_FOLD_RANKNORM, RD_NESTED); pg.combine = CB_MAX_RHAT; break;
+  }
+  return execute(ctx, x, mem, dtype, draws, chains, params, split_chains, pg, nullptr, rhat_out, nullptr);
+}
+
+static int transform_call(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains,
+                          int64_t params, int tr, int elem_bytes, void* out) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->err.clear();
+  if (!out) return fail(ctx, MCD_EINVAL, "output is NULL");
+  Program pg;
+  pg.want_arr = true; pg.arr_elem_bytes = elem_bytes;
+  pg.add(tr, RD_STORE);
+  return execute(ctx, x, mem, dtype, draws, chains, params, 1, pg, nullptr, nullptr, out);
+}
+
+int mcd_tiedrank(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,
+                 double* ranks_out) {
+  return transform_call(ctx, x, mem, dtype, draws, chains, params, TR_TIEDRANK, 8, ranks_out);
+}
+int mcd_rank_normalize(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains,
+                       int64_t params, void* out) {
+  return transform_call(ctx, x, mem, dtype, draws, chains, params, TR_RANKNORM, dtype == MCD_F64 ? 8 : 4, out);
+}
+int mcd_fold_around_median(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains,
+                           int64_t params, void* out) {
+  return transform_call(ctx, x, mem, dtype, draws, chains, params, TR_FOLD, dtype == MCD_F64 ? 8 : 4, out);
+}
+
+int mcd_generate_ar1(mcd_ctx* ctx, int dtype, int64_t draws, int64_t chains, int64_t params, int64_t param_offset,
+                     double phi, double sigma, uint64_t seed, void* dev_x) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->err.clear();
+  if (!dev_x || draws <= 0 || chains <= 0 || params < 0) return fail(ctx, MCD_EINVAL, "bad argument");
+  CU(cudaSetDevice(ctx->device));
+  long long series = chains * params;
+  if (series == 0) return MCD_OK;
+  long long blocks = (series + 127) / 128;
+  if (dtype == MCD_F64)
+    ar1_kernel<double><<<(unsigned)blocks, 128, 0, ctx->stream>>>((double*)dev_x, draws, chains, params, param_offset, phi, sigma, seed);
+  else if (dtype == MCD_F32)
+    ar1_kernel<float><<<(unsigned)blocks, 128, 0, ctx->stream>>>((float*)dev_x, draws, chains, params, param_offset, phi, sigma, seed);
+  else return fail(ctx, MCD_EINVAL, "bad dtype");
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return MCD_OK;
+}
+
+int mcd_device_alloc(mcd_ctx* ctx, int64_t bytes, void** dev_ptr) {
+  if (!ctx || !dev_ptr || bytes < 0) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMalloc(dev_ptr, (size_t)std::max<int64_t>(bytes, 1)));
+  return MCD_OK;
+}
+int mcd_device_free(mcd_ctx* ctx, void* dev_ptr) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaFree(dev_ptr));
+  return MCD_OK;
+}
+int mcd_memcpy_h2d(mcd_ctx* ctx, void* dev_dst, const void* host_src, int64_t bytes) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(dev_dst, host_src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MCD_OK;
+}
+int mcd_memcpy_d2h(mcd_ctx* ctx, void* host_dst, const void* dev_src, int64_t bytes) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(host_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MCD_OK;
+}
+int mcd_host_alloc(mcd_ctx* ctx, int64_t bytes, void** host_ptr) {
+  if (!ctx || !host_ptr || bytes < 0) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaHostAlloc(host_ptr, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+  return MCD_OK;
+}
+int mcd_host_free(mcd_ctx* ctx, void* host_ptr) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaFreeHost(host_ptr));
+  return MCD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+// mcd_common.cuh — device helpers shared by the slab (shared-memory) and large-slab
+// (global-memory) kernels of libmcmcdiag_b200.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace mcd {
+
+constexpr int WARP = 32;
+
+// ---------------------------------------------------------------------------------------
+// status flags raised by kernels (one word per context, read back after the call)
+// ---------------------------------------------------------------------------------------
+enum : unsigned {
+  FLAG_NAN_QUANTILE = 1u,   // quantile requested on a slab containing NaN (Julia throws)
+  FLAG_SORT_FALLBACK = 2u,  // at least one slab used the full-sort fallback (statistics only)
+};
+
+// ---------------------------------------------------------------------------------------
+// type traits
+// ---------------------------------------------------------------------------------------
+template <typename T> struct Traits;
+template <> struct Traits<double> {
+  using Key = unsigned long long;
+  static constexpr Key KEY_NAN = ~0ull;
+  __device__ static double nan() { return __longlong_as_double(0x7ff8000000000000ll); }
+};
+template <> struct Traits<float> {
+  using Key = unsigned int;
+  static constexpr Key KEY_NAN = ~0u;
+  __device__ static float nan() { return __int_as_float(0x7fc00000); }
+};
+
+// Order-preserving map float -> unsigned: isless order, except that -0.0 and 0.0 are
+// merged (they tie under `==`, which is what tiedrank's run detection uses) and every NaN
+// maps to the single largest key (NaNs rank last; their mutual order is by index and is
+// handled by the callers).
+__device__ __forceinline__ unsigned long long order_key(double v) {
+  if (v != v) return ~0ull;
+  long long b = __double_as_longlong(v + 0.0);
+  unsigned long long u = (unsigned long long)b;
+  return (b < 0) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ unsigned int order_key(float v) {
+  if (v != v) return ~0u;
+  int b = __float_as_int(v + 0.0f);
+  unsigned int u = (unsigned int)b;
+  return (b < 0) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ double key_value(unsigned long long k) {
+  unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ float key_value(unsigned int k) {
+  unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __int_as_float((int)u);
+}
+
+// Julia's min/max propagate NaN (src/ess_rhat.jl:574,591,594); fmin/fmax do not.
+template <typename T> __device__ __forceinline__ T jl_min(T a, T b) {
+  if (a != a || b != b) return Traits<T>::nan();
+  return a < b ? a : b;
+}
+template <typename T> __device__ __forceinline__ T jl_max(T a, T b) {
+  if (a != a || b != b) return Traits<T>::nan();
+  return a > b ? a : b;
+}
+
+// ---------------------------------------------------------------------------------------
+// warp / block reductions with a fixed tree (deterministic, batch-invariant)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum; `scratch` holds >= 33 doubles.  All threads get the result.
+// Contains two __syncthreads(); must be called by every thread of the block.
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  constexpr int NW = THREADS / WARP;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect scratch from a previous use
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double s = (lane < NW) ? scratch[lane] : 0.0;
+    s = warp_sum(s);
+    if (lane == 0) scratch[32] = s;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+// ---------------------------------------------------------------------------------------
+// special functions
+// ---------------------------------------------------------------------------------------
+// z for a doubled rank r2 = 2*rank (rank in 1..n, half-integers allowed), as the reference
+// computes it (src/utils.jl:189-193 then :182): q = (r - 3/8)/(n + 1/4) in Float64, stored
+// as T, z = norminvcdf(q) in T.
+template <typename T> __device__ __forceinline__ T z_from_rank2(long long r2, long long n) {
+  double q = (0.5 * (double)r2 - 0.375) / ((double)n + 0.25);
+  if (sizeof(T) == 4) {
+    float qf = (float)q;
+    return (T)(float)normcdfinv((double)qf);
+  }
+  return (T)normcdfinv(q);
+}
+
+// log of the complete beta function
+__device__ __forceinline__ double lbeta(double a, double b) { return lgamma(a) + lgamma(b) - lgamma(a + b); }
+
+// continued fraction for the incomplete beta function (modified Lentz)
+__device__ inline double betacf(double a, double b, double x) {
+  const double FPMIN = 1e-300, EPS = 1e-16;
+  double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 - qab * x / qap;
+  if (fabs(d) < FPMIN) d = FPMIN;
+  d = 1.0 / d;
+  double h = d;
+  for (int m = 1; m <= 20000; ++m) {
+    double m2 = 2.0 * m;
+    double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+    d = 1.0 + aa * d; if (fabs(d) < FPMIN) d = FPMIN;
+    c = 1.0 + aa / c; if (fabs(c) < FPMIN) c = FPMIN;
+    d = 1.0 / d; h *= d * c;
+    aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+    d = 1.0 + aa * d; if (fabs(d) < FPMIN) d = FPMIN;
+    c = 1.0 + aa / c; if (fabs(c) < FPMIN) c = FPMIN;
+    d = 1.0 / d;
+    double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < EPS) break;
+  }
+  return h;
+}
+
+// regularised incomplete beta I_x(a,b)
+__device__ inline double betainc_reg(double a, double b, double x) {
+  if (x <= 0.0) return 0.0;
+  if (x >= 1.0) return 1.0;
+  double lbt = a * log(x) + b * log1p(-x) - lbeta(a, b);
+  if (x < (a + 1.0) / (a + b + 2.0)) return exp(lbt) * betacf(a, b, x) / a;
+  return 1.0 - exp(lbt) * betacf(b, a, 1.0 - x) / b;
+}
+
+// inverse of I_x(a,b) = p  (StatsFuns.betainvcdf, call site src/mcse.jl:108-109).
+// Safeguarded Newton from the normal approximation; bracket kept for bisection.
+__device__ inline double betainc_inv(double a, double b, double p) {
+  if (!(a > 0.0) || !(b > 0.0) || !(p == p)) return CUDART_NAN;
+  if (p <= 0.0) return 0.0;
+  if (p >= 1.0) return 1.0;
+  double mu = a / (a + b);
+  double sd = sqrt(a * b / ((a + b) * (a + b) * (a + b + 1.0)));
+  double x = mu + normcdfinv(p) * sd;
+  double lo = 0.0, hi = 1.0;
+  if (!(x > 0.0 && x < 1.0)) x = mu;
+  const double lb = lbeta(a, b);
+  for (int it = 0; it < 200; ++it) {
+    double f = betainc_reg(a, b, x) - p;
+    if (f > 0.0) hi = x; else lo = x;
+    if (f == 0.0) break;
+    double lpdf = (a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lb;
+    double dx = f / exp(lpdf);
+    double xn = x - dx;
+    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+    if (fabs(xn - x) <= 4e-16 * fabs(xn) || hi - lo <= 1e-17) { x = xn; break; }
+    x = xn;
+  }
+  return x;
+}
+
+// Split-chain addressing (copyto_split!, src/utils.jl:13-41).  Split chain j = c*split + k
+// of a slab (draws x chains, chain-contiguous) starts at element
+//   c*draws + k*niter + min(k, draws % split)
+// and holds niter = draws / split consecutive elements.
+struct SplitGeom {
+  int draws, chains, split, niter, nch, n, rem;
+  __host__ __device__ SplitGeom() {}
+  __host__ __device__ SplitGeom(int draws_, int chains_, int split_)
+      : draws(draws_), chains(chains_), split(split_) {
+    niter = draws / split;
+    rem = draws % split;
+    nch = chains * split;
+    n = draws * chains;
+  }
+  __host__ __device__ __forceinline__ int chain_start(int j) const {
+    int c = j / split, k = j - c * split;
+    return c * draws + k * niter + (k < rem ? k : rem);
+  }
+};
+
+}  // namespace mcd
