@@ -80,9 +80,10 @@ const char* mcd_last_error(const mcd_ctx* ctx);
 const char* mcd_create_error(void);
 int mcd_abi_version(void);
 
-/* Run device work of subsequent MCD_DEVICE calls on this cudaStream_t (NULL = the
- * context's own stream).  The caller keeps ownership of the stream. */
-int mcd_set_stream(mcd_ctx* ctx, void* cuda_stream);
+/* Run the device work of subsequent calls on the caller's cudaStream_t `cuda_stream`
+ * (NULL is CUDA's default stream), or, with use_own != 0, on the context's own
+ * non-blocking stream (the initial state).  The caller keeps ownership of its stream. */
+int mcd_set_stream(mcd_ctx* ctx, void* cuda_stream, int use_own);
 /* Block until all work queued by this context has finished. */
 int mcd_synchronize(mcd_ctx* ctx);
 

@@ -33,7 +33,7 @@ SIGNATURES = {
     "mcd_create": (_int, [C.POINTER(_vp), _int]),
     "mcd_destroy": (None, [_vp]),
     "mcd_last_error": (C.c_char_p, [_vp]),
-    "mcd_set_stream": (_int, [_vp, _vp]),
+    "mcd_set_stream": (_int, [_vp, _vp, _int]),
     "mcd_synchronize": (_int, [_vp]),
     "mcd_set_option": (_int, [_vp, C.c_char_p, _i64]),
     "mcd_get_stat": (_i64, [_vp, C.c_char_p]),

@@ -135,7 +135,9 @@ class Context:
         return int(self._lib.mcd_get_stat(self._h, key.encode()))
 
     def set_stream(self, cuda_stream: int | None):
-        self.check(self._lib.mcd_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """cuda_stream: a cudaStream_t handle (0 = CUDA's default stream); None = the context's own stream."""
+        own = cuda_stream is None
+        self.check(self._lib.mcd_set_stream(self._h, C.c_void_p(0 if own else cuda_stream), int(own)))
 
     def synchronize(self):
         self.check(self._lib.mcd_synchronize(self._h))

@@ -158,6 +158,13 @@ struct Program {
   }
 };
 
+// log10(oftype(one(T), ntotal)) (src/ess_rhat.jl:514), correctly rounded: glibc's double
+// log10 is not (log10(40.0) is off by one ulp), so evaluate in long double and round once.
+template <typename T> static T rel_ess_max_of(long long ntotal) {
+  if (sizeof(T) == 8) return (T)(double)log10l((long double)ntotal);
+  return (T)(float)log10((double)(float)ntotal);
+}
+
 static int next_pow2(long long v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 static long long nextprod23(long long n) {
@@ -252,8 +259,7 @@ static int run_slab(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   a.combine = pg.combine; a.method = pg.method; a.maxlag = pg.maxlag; a.relative = pg.relative;
   a.ess_nan = pg.ess_nan;
   const long long ntotal = (long long)g.niter * g.nch;
-  if (sizeof(T) == 8) a.rel_ess_max = (T)log10((double)ntotal);
-  else a.rel_ess_max = (T)log10f((float)ntotal);
+  a.rel_ess_max = rel_ess_max_of<T>(ntotal);
   a.ess_out = d_ess; a.rhat_out = d_rhat; a.arr_out = d_arr;
   a.nbuckets = std::min(std::max(next_pow2(g.n), SLAB_THREADS), 16384);
   a.bucket_limit = ctx->bucket_limit;
@@ -309,6 +315,7 @@ static int run_device(mcd_ctx* ctx, const T* dx, long long params, const SplitGe
   env.workspace_bytes = ctx->workspace_bytes; env.launches = &ctx->launches;
   env.work = &ctx->work; env.work_cap = &ctx->work_cap; env.smem_optin = ctx->smem_optin;
   env.d_chain_inds = ctx->d_chain_inds;
+  env.rel_ess_max = (double)rel_ess_max_of<T>((long long)g.niter * g.nch);
   std::string msg;
   int rc = run_large<T>(env, dx, params, g, pg.nsteps, pg.steps, pg.combine, pg.method, pg.maxlag, pg.relative,
                         pg.ess_nan, pg.mcse_p, (int)pg.cps, (int)pg.nsuper, d_ess, d_rhat, d_arr, msg);
@@ -499,10 +506,10 @@ void mcd_destroy(mcd_ctx* ctx) {
 
 const char* mcd_last_error(const mcd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
-int mcd_set_stream(mcd_ctx* ctx, void* cuda_stream) {
+int mcd_set_stream(mcd_ctx* ctx, void* cuda_stream, int use_own) {
   if (!ctx) return MCD_EINVAL;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  ctx->stream = use_own ? ctx->own_stream : (cudaStream_t)cuda_stream;
   return MCD_OK;
 }
 
