@@ -87,11 +87,11 @@ int mcd_set_stream(mcd_ctx* ctx, void* cuda_stream, int use_own);
 /* Block until all work queued by this context has finished. */
 int mcd_synchronize(mcd_ctx* ctx);
 
-/* Tuning / test knobs.  Keys: "force_path" (0 auto, 1 shared-memory slab kernel,
- * 2 global-memory large-slab pipeline), "h2d_chunk_bytes", "workspace_bytes",
- * "sort_bucket_limit". */
+/* Tuning / test knobs.  Keys: "force_path" (0 auto, 1 general shared-memory slab kernel,
+ * 2 global-memory large-slab pipeline, 3 register-resident fast kernel only),
+ * "h2d_chunk_bytes", "workspace_bytes", "sort_bucket_limit". */
 int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value);
-/* Counters.  Keys: "kernel_launches" (since creation), "last_path" (1 slab, 2 large),
+/* Counters.  Keys: "kernel_launches" (since creation), "last_path" (1 slab, 2 large, 3 fast),
  * "h2d_bytes", "d2h_bytes", "sm_count". */
 int64_t mcd_get_stat(const mcd_ctx* ctx, const char* key);
 

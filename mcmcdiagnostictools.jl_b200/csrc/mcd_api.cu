@@ -5,6 +5,7 @@
 #include "../../include/mcmcdiag_b200.h"
 #include "mcd_common.cuh"
 #include "mcd_slab.cuh"
+#include "mcd_fast.cuh"
 #include "mcd_large.cuh"
 
 #include <algorithm>
@@ -34,6 +35,7 @@ struct mcd_ctx {
   void* tw = nullptr; int tw_n = 0; int tw_dtype = -1; size_t tw_cap = 0;
   unsigned* d_flags = nullptr;
   int* d_chain_inds = nullptr; size_t chain_inds_cap = 0;
+  int* d_redo = nullptr; size_t redo_cap = 0;   // [0] = count, [1..] = parameter indices
   // staging / workspace
   void* stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0};
   void* d_out[2] = {nullptr, nullptr}; size_t out_cap[2] = {0, 0};
@@ -227,9 +229,11 @@ static size_t slab_layout(SlabArgs<T>& a, const Program& pg) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (int)o; };
   a.offX = take((size_t)n * ts);
-  a.offY = take((size_t)n * ts);
+  // single-step programs never look at the raw slab again: transform in place (Y aliases X)
+  const bool alias_xy = pg.nsteps == 1 && pg.combine == CB_PLAIN;
+  a.offY = alias_xy ? a.offX : take((size_t)n * ts);
   a.offK = take((size_t)n * ts);
-  a.offCNT = take((size_t)a.nbuckets * 4);
+  a.offCNT = take((size_t)(a.nbuckets + SLAB_THREADS) * 4);
   size_t view_bytes = off - (size_t)a.offK;
   a.offCM = take((size_t)a.g.nch * ts);
   a.offCV = take((size_t)a.g.nch * ts);
@@ -249,7 +253,8 @@ static size_t slab_layout(SlabArgs<T>& a, const Program& pg) {
 
 template <typename T>
 static int run_slab(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom& g, const Program& pg,
-                    T* d_ess, T* d_rhat, void* d_arr, bool* handled) {
+                    T* d_ess, T* d_rhat, void* d_arr, bool* handled, const int* redo_list = nullptr,
+                    const int* redo_count = nullptr) {
   *handled = false;
   SlabArgs<T> a;
   memset(&a, 0, sizeof a);
@@ -267,6 +272,7 @@ static int run_slab(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   a.cps = (int)pg.cps; a.nsuper = (int)pg.nsuper;
   a.mcse_p = pg.mcse_p;
   a.flags = ctx->d_flags;
+  a.redo_list = redo_list; a.redo_count = redo_count;
   if (g.nch > 4096 || pg.nsuper > 4096) return MCD_OK;
   const size_t smem = slab_layout<T>(a, pg);
   if (smem > (size_t)ctx->smem_optin) return MCD_OK;  // not handled: caller uses the large path
@@ -287,12 +293,68 @@ static int run_slab(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   auto kern = slab_kernel<T, SLAB_THREADS>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long grid = std::min<long long>(params, 1ll << 30);
+  if (redo_list) grid = std::min<long long>(grid, 2ll * ctx->sm_count);
   if (grid > 0) {
     kern<<<(unsigned)grid, SLAB_THREADS, smem, ctx->stream>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
   }
-  ctx->last_path = 1;
+  if (!redo_list) ctx->last_path = 1;
+  *handled = true;
+  return MCD_OK;
+}
+
+// The register-resident fast kernel (mcd_fast.cuh) for 8 split chains of <= 512 draws.
+template <typename T>
+static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom& g, const Program& pg,
+                    T* d_ess, T* d_rhat, bool* handled) {
+  *handled = false;
+  if (g.nch != FAST_NCH || g.rem != 0 || g.niter < 2 || g.niter > FAST_MAXITER || params >= (1ll << 31)) return MCD_OK;
+  if (pg.want_arr || pg.chain_inds) return MCD_OK;
+  const bool ess_live = pg.want_ess && !pg.ess_nan;
+  if (ess_live && pg.method != MCD_AUTOCOV_DIRECT) return MCD_OK;
+  FastArgs<T> a;
+  memset(&a, 0, sizeof a);
+  const Step& s0 = pg.steps[0];
+  if (pg.nsteps == 1 && pg.combine == CB_PLAIN && (s0.transform == TR_NONE || s0.transform == TR_RANKNORM) &&
+      (s0.reduce == RD_ESS_RHAT || s0.reduce == RD_RHAT)) {
+    a.do_bulk = 1; a.rank_x = s0.transform == TR_RANKNORM; a.want_ess = s0.reduce == RD_ESS_RHAT;
+  } else if (pg.nsteps == 1 && pg.combine == CB_PLAIN && s0.transform == TR_FOLD_RANKNORM && s0.reduce == RD_RHAT) {
+    a.do_tail = 1;
+  } else if (pg.nsteps == 2 && pg.combine == CB_RANK && s0.transform == TR_RANKNORM &&
+             (s0.reduce == RD_ESS_RHAT || s0.reduce == RD_RHAT) && pg.steps[1].transform == TR_FOLD_RANKNORM &&
+             pg.steps[1].reduce == RD_RHAT) {
+    a.do_bulk = 1; a.rank_x = 1; a.want_ess = s0.reduce == RD_ESS_RHAT; a.do_tail = 1;
+  } else return MCD_OK;
+  a.x = dx; a.params = params; a.niter = g.niter;
+  a.maxlag = pg.maxlag; a.relative = pg.relative; a.ess_nan = pg.ess_nan;
+  a.rel_ess_max = rel_ess_max_of<T>((long long)g.niter * g.nch);
+  a.ess_out = d_ess; a.rhat_out = d_rhat;
+  a.nbuckets = std::min(std::max(next_pow2(2ll * g.n), 1024), 8192);
+  a.bucket_limit = ctx->bucket_limit;
+  const int dtype = sizeof(T) == 8 ? MCD_F64 : MCD_F32;
+  if (a.rank_x || a.do_tail) {
+    int rc = ensure_ztab(ctx, dtype, g.n);
+    if (rc) return rc;
+    a.ztab = (const T*)ctx->ztab;
+  }
+  int rc = ensure_cap(ctx, (void**)&ctx->d_redo, &ctx->redo_cap, (size_t)(params + 1) * sizeof(int));
+  if (rc) return rc;
+  a.redo_count = ctx->d_redo; a.redo_list = ctx->d_redo + 1;
+  CU(cudaMemsetAsync(ctx->d_redo, 0, sizeof(int), ctx->stream));
+  const size_t big = std::max<size_t>((size_t)FAST_NCH * FAST_ROW * 8, (size_t)(2 * FAST_NCH * FAST_MAXITER + a.nbuckets + 4) * 4);
+  const size_t smem = align_up(big, 16) + 128 + 64 * 8 + 16 * 8 + 4 * 8 + 8 * 4 + (size_t)(pg.maxlag + 9) * sizeof(T) + 64;
+  auto kern = fast_kernel<T>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  // slabs the fast kernel declined (NaN, infinite range, heavy ties): general slab kernel
+  bool h2 = false;
+  rc = run_slab<T>(ctx, dx, params, g, pg, d_ess, d_rhat, nullptr, &h2, ctx->d_redo + 1, ctx->d_redo);
+  if (rc) return rc;
+  if (!h2) return fail(ctx, MCD_EUNSUPPORTED, "internal: redo kernel unavailable");
+  ctx->last_path = 3;
   *handled = true;
   return MCD_OK;
 }
@@ -303,6 +365,12 @@ static int run_device(mcd_ctx* ctx, const T* dx, long long params, const SplitGe
                       T* d_ess, T* d_rhat, void* d_arr) {
   if (params == 0) return MCD_OK;
   bool handled = false;
+  if (ctx->force_path == 0 || ctx->force_path == 3) {
+    int rc = run_fast<T>(ctx, dx, params, g, pg, d_ess, d_rhat, &handled);
+    if (rc) return rc;
+    if (handled) return MCD_OK;
+    if (ctx->force_path == 3) return fail(ctx, MCD_EUNSUPPORTED, "this call is outside the fast kernel's shapes/programs");
+  }
   if (ctx->force_path != 2) {
     int rc = run_slab<T>(ctx, dx, params, g, pg, d_ess, d_rhat, d_arr, &handled);
     if (rc) return rc;
@@ -492,7 +560,7 @@ void mcd_destroy(mcd_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  void* ptrs[] = {ctx->ztab, ctx->tw, ctx->d_flags, ctx->d_chain_inds, ctx->stage[0], ctx->stage[1],
+  void* ptrs[] = {ctx->ztab, ctx->tw, ctx->d_flags, ctx->d_chain_inds, ctx->d_redo, ctx->stage[0], ctx->stage[1],
                   ctx->d_out[0], ctx->d_out[1], ctx->d_arr, ctx->work};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
@@ -526,7 +594,7 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return MCD_EINVAL;
   std::lock_guard<std::mutex> lk(ctx->mu);
   std::string k(key);
-  if (k == "force_path") { if (value < 0 || value > 2) return fail(ctx, MCD_EINVAL, "force_path in 0..2"); ctx->force_path = (int)value; }
+  if (k == "force_path") { if (value < 0 || value > 3) return fail(ctx, MCD_EINVAL, "force_path in 0..3"); ctx->force_path = (int)value; }
   else if (k == "h2d_chunk_bytes") { if (value < 1) return fail(ctx, MCD_EINVAL, "h2d_chunk_bytes >= 1"); ctx->h2d_chunk_bytes = value; }
   else if (k == "workspace_bytes") { if (value < (1 << 20)) return fail(ctx, MCD_EINVAL, "workspace_bytes >= 1 MiB"); ctx->workspace_bytes = value; }
   else if (k == "sort_bucket_limit") { if (value < 0) return fail(ctx, MCD_EINVAL, "sort_bucket_limit >= 0"); ctx->bucket_limit = (int)value; }

@@ -74,6 +74,8 @@ template <typename T> struct SlabArgs {
   int cps, nsuper;
   double mcse_p;
   unsigned* flags;
+  const int* redo_list;   // when set: recompute only these parameters (fast-kernel fallbacks)
+  const int* redo_count;
   // shared-memory byte offsets
   int offX, offY, offK, offCNT, offCM, offCV, offGAM, offGSUM, offPART, offFFT, offMISC;
 };
@@ -107,6 +109,10 @@ template <typename T> __device__ __forceinline__ int bucket_of(T v, double vmin,
   b = b < 0 ? 0 : b;
   return b >= B ? B - 1 : b;
 }
+
+// Bucket counters are stored padded, one extra word per scan chunk (B / THREADS buckets), so
+// that the per-thread sequential scan strides by an odd number of words (conflict-free).
+__device__ __forceinline__ int cidx(int b, int per_shift) { return b + (b >> per_shift); }
 
 // Ascending bitonic network with virtual +inf padding: every comparator puts the smaller
 // key at the lower index, so comparators whose upper index is >= n are no-ops.
@@ -187,12 +193,13 @@ __device__ void build_view(const T* V, int n, T* K, unsigned* CNT, int B, int li
   int mode = ms->vs.mode;
   if (mode == VM_BUCKET) {
     const double vmin = ms->vs.vmin, scale = ms->vs.scale;
-    for (int i = tid; i < B; i += THREADS) CNT[i] = 0;
+    const int psh = 31 - __clz(B / THREADS);
+    for (int i = tid; i < B + THREADS; i += THREADS) CNT[i] = 0;
     __syncthreads();
     int lmaxc = 0;
     for (int i = tid; i < n; i += THREADS) {
       int b = bucket_of<T>(V[i], vmin, scale, B);
-      int old = (int)atomicAdd(&CNT[b], 1u);
+      int old = (int)atomicAdd(&CNT[cidx(b, psh)], 1u);
       lmaxc = old + 1 > lmaxc ? old + 1 : lmaxc;
     }
     lmaxc = warp_max(lmaxc);
@@ -209,8 +216,9 @@ __device__ void build_view(const T* V, int n, T* K, unsigned* CNT, int B, int li
     if (mode == VM_BUCKET) {
       // exclusive scan of CNT[0..B): thread t owns a contiguous chunk
       const int per = B / THREADS;
+      unsigned* mine = CNT + tid * (per + 1);   // = CNT + cidx(tid * per)
       unsigned s = 0;
-      for (int i = 0; i < per; ++i) s += CNT[tid * per + i];
+      for (int i = 0; i < per; ++i) s += mine[i];
       unsigned incl = s;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -223,8 +231,8 @@ __device__ void build_view(const T* V, int n, T* K, unsigned* CNT, int B, int li
       for (int i = 0; i < w; ++i) woff += (unsigned)ms->wred_i[i];
       unsigned run = woff + incl - s;
       for (int i = 0; i < per; ++i) {
-        unsigned c = CNT[tid * per + i];
-        CNT[tid * per + i] = run;
+        unsigned c = mine[i];
+        mine[i] = run;
         run += c;
       }
       __syncthreads();
@@ -232,7 +240,7 @@ __device__ void build_view(const T* V, int n, T* K, unsigned* CNT, int B, int li
       for (int i = tid; i < n; i += THREADS) {
         T v = V[i];
         int b = bucket_of<T>(v, vmin, scale, B);
-        unsigned pos = atomicAdd(&CNT[b], 1u);
+        unsigned pos = atomicAdd(&CNT[cidx(b, psh)], 1u);
         K[pos] = v;
       }
       __syncthreads();
@@ -255,8 +263,9 @@ __device__ __forceinline__ int view_rank2(T v, int n, const T* K, const unsigned
                                           const ViewState& vs) {
   using Key = typename Traits<T>::Key;
   if (vs.mode == VM_BUCKET) {
+    const int psh = 31 - __clz(B / (int)blockDim.x);
     int b = bucket_of<T>(v, vs.vmin, vs.scale, B);
-    int s = b ? (int)CNT[b - 1] : 0, e = (int)CNT[b];
+    int s = b ? (int)CNT[cidx(b - 1, psh)] : 0, e = (int)CNT[cidx(b, psh)];
     int less = 0, eq = 0;
     for (int j = s; j < e; ++j) {
       T y = K[j];
@@ -283,9 +292,10 @@ __device__ T view_select(int k, int n, const T* K, const unsigned* CNT, int B, c
   using Key = typename Traits<T>::Key;
   if (vs.mode == VM_CONST) return (T)vs.vmin;
   if (vs.mode == VM_SORTED) return key_value(reinterpret_cast<const Key*>(K)[k]);
+  const int psh = 31 - __clz(B / (int)blockDim.x);
   int lo = 0, hi = B - 1;  // smallest b with CNT[b] > k
-  while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)CNT[mid] > k) hi = mid; else lo = mid + 1; }
-  const int s = lo ? (int)CNT[lo - 1] : 0, e = (int)CNT[lo];
+  while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)CNT[cidx(mid, psh)] > k) hi = mid; else lo = mid + 1; }
+  const int s = lo ? (int)CNT[cidx(lo - 1, psh)] : 0, e = (int)CNT[cidx(lo, psh)];
   const int target = k - s;
   for (int j = s; j < e; ++j) {
     T y = K[j];
@@ -671,7 +681,9 @@ __global__ void __launch_bounds__(THREADS) slab_kernel(const SlabArgs<T> a) {
   const SplitGeom& g = a.g;
   const int n = g.n, tid = threadIdx.x, B = a.nbuckets;
 
-  for (long long param = blockIdx.x; param < a.params; param += gridDim.x) {
+  const long long work = a.redo_list ? (long long)*a.redo_count : a.params;
+  for (long long item = blockIdx.x; item < work; item += gridDim.x) {
+    const long long param = a.redo_list ? (long long)a.redo_list[item] : item;
     const T* __restrict__ src = a.x + param * (long long)n;
     for (int i = tid; i < n; i += THREADS) X[i] = __ldg(&src[i]);
     __syncthreads();
@@ -685,8 +697,10 @@ __global__ void __launch_bounds__(THREADS) slab_kernel(const SlabArgs<T> a) {
       bool want_rank_store = false;
       switch (st.transform) {
         case TR_NONE:
-          for (int i = tid; i < n; i += THREADS) Y[i] = X[i];
-          __syncthreads();
+          if (Y != X) {
+            for (int i = tid; i < n; i += THREADS) Y[i] = X[i];
+            __syncthreads();
+          }
           break;
         case TR_RANKNORM:
         case TR_TIEDRANK:

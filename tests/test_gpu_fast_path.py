@@ -1,0 +1,137 @@
+"""The register-resident fast kernel (mcd_fast.cuh: 8 split chains of <= 512 draws, one warp per
+split chain) against the oracle and against the general slab kernel, including the slabs it
+hands back to the general kernel (NaN, infinities, heavy ties, constants)."""
+import numpy as np
+import pytest
+from scipy import stats
+
+pytestmark = pytest.mark.gpu
+RTOL64, RTOL32 = 1e-8, 1e-4
+
+
+@pytest.fixture(scope="module")
+def o():
+    from oracle import mcmcdiag_oracle
+    return mcmcdiag_oracle
+
+
+@pytest.fixture()
+def mcd():
+    import mcmcdiag_b200 as m
+    ctx = m.get_context(0)
+    ctx.set_option("force_path", 0)
+    yield m
+    ctx.set_option("force_path", 0)
+
+
+def rng(s):
+    return np.random.default_rng(s)
+
+
+def close(a, b, rtol):
+    return np.allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=rtol, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("shape,split", [((1000, 4), 2), ((500, 8), 1), ((1024, 4), 2), ((64, 4), 2), ((300, 2), 4),
+                                          ((999, 8), 1), ((10, 4), 2), ((1002, 4), 2)])
+@pytest.mark.parametrize("kind", ["rank", "bulk", "tail", "basic"])
+def test_fast_shapes(mcd, o, shape, split, kind):
+    x = o.ar1(0.5, np.sqrt(0.75), shape[0], shape[1], 12, rng=rng(51))
+    ctx = mcd.get_context(0)
+    fast_ok = shape[0] % split == 0 and shape[0] // split <= 512
+    for maxlag in (250, 9, 2, 1):
+        S, R = mcd.ess_rhat(x, kind=kind, split_chains=split, maxlag=maxlag)
+        if kind != "tail":
+            assert ctx.stat("last_path") == (3 if fast_ok else 1)
+        So, Ro = o.ess_rhat(x, kind=kind, split_chains=split, maxlag=maxlag)
+        assert close(S, So, RTOL64), (maxlag, S, So)
+        assert close(R, Ro, RTOL64)
+    Rr = mcd.rhat(x, kind=kind, split_chains=split)
+    assert ctx.stat("last_path") == (3 if fast_ok else 1)
+    assert close(Rr, o.rhat(x, kind=kind, split_chains=split), RTOL64)
+    if kind in ("bulk", "basic"):
+        assert close(mcd.ess(x, kind=kind, split_chains=split), o.ess(x, kind=kind, split_chains=split), RTOL64)
+
+
+@pytest.mark.parametrize("phi", [-0.9, -0.3, 0.0, 0.9, 0.99])
+def test_fast_phi(mcd, o, phi):
+    x = o.ar1(phi, np.sqrt(1 - phi ** 2), 1000, 4, 16, rng=rng(52))
+    S, R = mcd.ess_rhat(x)
+    So, Ro = o.ess_rhat(x)
+    assert close(S, So, RTOL64) and close(R, Ro, RTOL64)
+    S, R = mcd.ess_rhat(x, relative=True)
+    assert close(S, So / 4000, RTOL64)
+
+
+def test_fast_matches_general_kernel(mcd):
+    x = rng(53).standard_normal((1000, 4, 64))
+    ctx = mcd.get_context(0)
+    out = {}
+    for path in (3, 1):
+        ctx.set_option("force_path", path)
+        out[path] = [mcd.ess_rhat(x, kind=k) for k in ("rank", "bulk", "basic")] + [(None, mcd.rhat(x, kind="tail"))]
+    for (S3, R3), (S1, R1) in zip(out[3], out[1]):
+        if S3 is not None:
+            assert close(S3, S1, 1e-11)
+        assert close(R3, R1, 1e-12)
+
+
+def test_fast_fallback_slabs(mcd, o):
+    r = rng(54)
+    x = r.standard_normal((1000, 4, 12))
+    x[3, 1, 1] = np.nan                      # NaN -> general kernel (ranks by index order)
+    x[:, :, 2] = 7.5                         # constant
+    x[:, :, 3] = r.integers(1, 6, (1000, 4))  # heavy ties -> bucket overflow -> general kernel
+    x[5, 2, 4] = np.inf
+    x[6, 3, 5] = -np.inf
+    x[:, :, 6] = np.round(x[:, :, 6], 2)     # light ties stay on the fast path
+    x[:, :, 7] *= 1e-300
+    x[:, :, 8] *= 1e300
+    x[:, :, 9] = stats.cauchy.ppf(stats.norm.cdf(x[:, :, 9]))
+    x[:10, :, 10] = 1e6                      # outliers squeeze the rest into few buckets
+    for kind in ("rank", "bulk", "basic"):
+        S, R = mcd.ess_rhat(x, kind=kind)
+        So, Ro = o.ess_rhat(x, kind=kind)
+        assert close(S, So, RTOL64), (kind, S, So)
+        assert close(R, Ro, RTOL64), (kind, R, Ro)
+    assert close(mcd.rhat(x, kind="tail"), o.rhat(x, kind="tail"), RTOL64)
+
+
+def test_fast_exact_anchors(mcd, o):
+    xn = rng(55).standard_normal((1000, 4, 10))
+    xc = stats.cauchy.ppf(stats.norm.cdf(xn))
+    assert np.array_equal(mcd.ess(xn, kind="bulk"), mcd.ess(xc, kind="bulk"))
+    xa = o.ar1(-0.9, np.sqrt(1 - 0.81), 100, 4, 500, rng=rng(56))
+    S = mcd.ess(xa, kind="basic")
+    assert S.max() == 400 * np.log10(400) and S.min() > 0
+    x = rng(57).standard_normal((1000, 4, 6, 2))
+    S, R = mcd.ess_rhat(x)
+    for i in range(2):
+        for j in range(6):
+            s, r_ = mcd.ess_rhat(x[:, :, j, i])
+            assert s == S[j, i] and r_ == R[j, i]
+    S1, R1 = mcd.ess_rhat(np.ones((1000, 4, 3)))
+    assert np.all(np.isnan(S1)) and np.all(np.isnan(R1))
+
+
+def test_fast_float32(mcd, o):
+    x = o.ar1(0.5, np.sqrt(0.75), 1000, 4, 32, rng=rng(58)).astype(np.float32)
+    for kind in ("rank", "bulk", "basic"):
+        S, R = mcd.ess_rhat(x, kind=kind)
+        assert mcd.get_context(0).stat("last_path") == 3
+        So, Ro = o.ess_rhat(x, kind=kind)
+        assert S.dtype == np.float32 and close(S, So, RTOL32) and close(R, Ro, RTOL32)
+    r = mcd.tiedrank(x)
+    for p in range(3):
+        assert np.array_equal(r[:, :, p].reshape(-1, order="F"), o.tiedrank(x[:, :, p].reshape(-1, order="F")))
+
+
+def test_fast_many_params_statistics(mcd, o):
+    """Parity reported as a fraction within tolerance (Geyer truncation is discontinuous)."""
+    x = mcd.generate_ar1(0.5, np.sqrt(0.75), 1000, 4, 3000, seed=7)
+    S, R = mcd.ess_rhat(x)
+    from oracle import ref_port as rp
+    So, Ro = rp.ess_rhat(x.cpu().numpy())
+    relS = np.abs(S.cpu().numpy() - So) / np.abs(So)
+    relR = np.abs(R.cpu().numpy() - Ro) / np.abs(Ro)
+    assert (relS < RTOL64).mean() == 1.0 and (relR < RTOL64).mean() == 1.0, (relS.max(), relR.max())
