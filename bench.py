@@ -172,21 +172,16 @@ def gpu_arm(args):
     ctx = mcd.get_context(local)
 
     total = args.params
-    lo, hi = rank * total // world, (rank + 1) * total // world
+    lo, hi = mcd.sharding.shard_range(total, rank, world)
     shard = hi - lo
     sigma = (1 - PHI * PHI) ** 0.5
     x = mcd.generate_ar1(PHI, sigma, DRAWS, CHAINS, shard, seed=1, param_offset=lo, device=local)
     torch.cuda.synchronize()
 
-    gathered = [torch.empty(2, (r + 1) * total // world - r * total // world, dtype=torch.float64, device=dev)
-                for r in range(world)] if (world > 1 and rank == 0) else None
-
     def step():
         S, R = mcd.ess_rhat(x, kind="rank")
         if world > 1:
-            out = torch.stack((S, R))
-            dist.gather(out, gathered, dst=0)
-            return gathered if rank == 0 else out
+            return mcd.sharding.gather_params(torch.stack((S, R)), total, dst=0)
         return S, R
 
     def barrier():
@@ -213,8 +208,7 @@ def gpu_arm(args):
         S, R = mcd.ess_rhat(x, kind="rank")
         kev[i][1].record()
         if world > 1:
-            out = torch.stack((S, R))
-            dist.gather(out, gathered, dst=0)
+            mcd.sharding.gather_params(torch.stack((S, R)), total, dst=0)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

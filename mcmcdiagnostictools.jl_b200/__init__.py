@@ -7,6 +7,6 @@ The directory name contains a dot, so import it through the root-level loader:
 """
 from .api import *  # noqa: F401,F403
 from .api import __all__  # noqa: F401
-from . import _lib, build  # noqa: F401
+from . import _lib, build, sharding  # noqa: F401
 
 __version__ = "0.1.0"

@@ -330,7 +330,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   a.maxlag = pg.maxlag; a.relative = pg.relative; a.ess_nan = pg.ess_nan;
   a.rel_ess_max = rel_ess_max_of<T>((long long)g.niter * g.nch);
   a.ess_out = d_ess; a.rhat_out = d_rhat;
-  a.nbuckets = std::min(std::max(next_pow2(2ll * g.n), 1024), 8192);
+  a.nbuckets = std::min(std::max(next_pow2(2ll * g.n), 2048), 8192);
   a.bucket_limit = ctx->bucket_limit;
   const int dtype = sizeof(T) == 8 ? MCD_F64 : MCD_F32;
   if (a.rank_x || a.do_tail) {

@@ -48,6 +48,15 @@ __device__ __forceinline__ unsigned int order_key(float v) {
   unsigned int u = (unsigned int)b;
   return (b < 0) ? ~u : (u | 0x80000000u);
 }
+// same map for values already known not to be NaN
+__device__ __forceinline__ unsigned long long order_key_nonan(double v) {
+  const long long b = __double_as_longlong(v + 0.0);
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+__device__ __forceinline__ unsigned int order_key_nonan(float v) {
+  const int b = __float_as_int(v + 0.0f);
+  return (unsigned int)(b ^ ((b >> 31) | (int)0x80000000u));
+}
 __device__ __forceinline__ double key_value(unsigned long long k) {
   unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
   return __longlong_as_double((long long)u);

@@ -47,7 +47,7 @@ template <typename T> struct FastArgs {
   T* ess_out;
   T* rhat_out;
   const T* ztab;        // [2n-1]
-  int nbuckets;         // multiple of 1024
+  int nbuckets;         // multiple of 2048
   int bucket_limit;
   int* redo_list;
   int* redo_count;
@@ -92,6 +92,23 @@ __device__ __forceinline__ double warp_reduce8(double (&a)[8]) {
   d += __shfl_xor_sync(0xffffffffu, d, 2);
   d += __shfl_xor_sync(0xffffffffu, d, 1);
   return d;  // lane l holds total of acc[(l >> 2)]: bit4 -> +4, bit3 -> +2, bit2 -> +1
+}
+
+// exact (less, eq) of an element inside its bucket on the full key; returns less | eq << 16.
+// Kept out of line: it runs only for elements whose hi word collides with a bucket-mate's.
+template <bool TWO>
+__device__ __noinline__ unsigned resolve_exact(const unsigned* Khi, const unsigned* Klo, int st, int c, unsigned vhi,
+                                               unsigned vlo) {
+  unsigned less = 0, eq = 0;
+  for (int j = st; j < st + c; ++j) {
+    const unsigned yhi = Khi[j];
+    if (TWO) {
+      const unsigned ylo = Klo[j];
+      less += (yhi < vhi) | ((yhi == vhi) & (ylo < vlo));
+      eq += (yhi == vhi) & (ylo == vlo);
+    } else { less += (yhi < vhi); eq += (yhi == vhi); }
+  }
+  return less | (eq << 16);
 }
 
 template <typename T>
@@ -207,33 +224,43 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
           if (__syncthreads_or(maxoff >= (unsigned)a.bucket_limit)) { redo = true; break; }
           // ---- scan: CNT[b] = start | count << 16 ---------------------------------------------------
           {
-            const int per_warp = B / FAST_NCH;       // buckets per warp, multiple of 128
+            const int per_warp = B / FAST_NCH;       // buckets per warp, multiple of 256
             unsigned carry = 0;
-            for (int it = 0; it < per_warp / 128; ++it) {
-              uint4* p4 = reinterpret_cast<uint4*>(CNT + w * per_warp + it * 128) + lane;
-              uint4 c4 = *p4;
+            // each lane owns 4 buckets in each of two consecutive 128-bucket groups; the two
+            // lane totals ride one 32-bit shuffle scan packed as 16-bit halves (n <= 4096)
+            for (int it = 0; it < per_warp / 256; ++it) {
+              uint4* p4 = reinterpret_cast<uint4*>(CNT + w * per_warp + it * 256) + lane;
+              uint4 c4 = p4[0], d4 = p4[32];
               const unsigned c0 = c4.x >> 16, c1 = c4.y >> 16, c2 = c4.z >> 16, c3 = c4.w >> 16;
-              const unsigned tot = c0 + c1 + c2 + c3;
+              const unsigned d0 = d4.x >> 16, d1 = d4.y >> 16, d2 = d4.z >> 16, d3 = d4.w >> 16;
+              const unsigned tot = (c0 + c1 + c2 + c3) | ((d0 + d1 + d2 + d3) << 16);
               unsigned incl = tot;
 #pragma unroll
               for (int o = 1; o < 32; o <<= 1) {
                 const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
               }
-              unsigned s0 = carry + incl - tot;
+              const unsigned all = __shfl_sync(0xffffffffu, incl, 31);
+              const unsigned excl = incl - tot;
+              unsigned s0 = carry + (excl & 0xffffu);
               c4.x = s0 | (c0 << 16); s0 += c0;
               c4.y = s0 | (c1 << 16); s0 += c1;
               c4.z = s0 | (c2 << 16); s0 += c2;
               c4.w = s0 | (c3 << 16);
-              *p4 = c4;
-              carry += __shfl_sync(0xffffffffu, incl, 31);
+              unsigned s1 = carry + (all & 0xffffu) + (excl >> 16);
+              d4.x = s1 | (d0 << 16); s1 += d0;
+              d4.y = s1 | (d1 << 16); s1 += d1;
+              d4.z = s1 | (d2 << 16); s1 += d2;
+              d4.w = s1 | (d3 << 16);
+              p4[0] = c4; p4[32] = d4;
+              carry += (all & 0xffffu) + (all >> 16);
             }
             if (lane == 0) iflag[w] = (int)carry;
             __syncthreads();
             unsigned woff = 0;
             for (int i = 0; i < w; ++i) woff += (unsigned)iflag[i];
             if (woff) {
-              for (int it = 0; it < per_warp / 128; ++it) {
+              for (int it = 0; it < per_warp / 128; ++it) {  // 128 buckets = 32 lanes x uint4
                 uint4* p4 = reinterpret_cast<uint4*>(CNT + w * per_warp + it * 128) + lane;
                 uint4 c4 = *p4;
                 c4.x += woff; c4.y += woff; c4.z += woff; c4.w += woff;
@@ -247,38 +274,64 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
           for (int k = 0; k < FAST_EPT; ++k) {
             if (lane + 32 * k < niter) {
               const unsigned pos = (CNT[bo[k] & 0xffffu] & 0xffffu) + (bo[k] >> 16);
-              const Key key = order_key(x[k]);
+              const Key key = order_key_nonan(x[k]);
               if (FastKeys<T>::TWO) { Khi[pos] = (unsigned)((unsigned long long)key >> 32); Klo[pos] = (unsigned)key; }
               else Khi[pos] = (unsigned)key;
             }
           }
           __syncthreads();
           // ---- resolve: exact doubled average rank, z lookup, median capture ------------------------
+          // Round r compares every element with the r-th member of its bucket, for all 16 elements
+          // of the thread at once (16 independent shared-memory gathers in flight).  The trip count
+          // is the warp-wide maximum bucket population; an element past its bucket end re-reads its
+          // own slot, which contributes nothing.  Only the 32-bit hi plane is gathered; a hi tie
+          // with another element (two values within 2^-20 relative) is settled exactly on (hi, lo)
+          // by resolve_exact().
           const int mA = (n & 1) ? n / 2 : n / 2 - 1, mB = n / 2;
+          unsigned vhi[FAST_EPT], acc[FAST_EPT];
+          int cm = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            if (lane + 32 * k < niter) {
-              const unsigned cw = CNT[bo[k] & 0xffffu];
-              const int s = (int)(cw & 0xffffu), e = s + (int)(cw >> 16);
-              const Key key = order_key(x[k]);
-              const unsigned vhi = FastKeys<T>::TWO ? (unsigned)((unsigned long long)key >> 32) : (unsigned)key;
-              const unsigned vlo = (unsigned)key;
-              int less = 0, eq = 0;
-              for (int j = s; j < e; ++j) {
-                const unsigned yhi = Khi[j];
-                if (FastKeys<T>::TWO) {
-                  if (yhi == vhi) { const unsigned ylo = Klo[j]; less += (ylo < vlo); eq += (ylo == vlo); }
-                  else less += (yhi < vhi);
-                } else { less += (yhi < vhi); eq += (yhi == vhi); }
-              }
-              const int lo = s + less, hi = lo + eq;
-              if (pass == 0 && a.do_tail) {
-                if (lo <= mA && mA < hi) thr[0] = (double)x[k];
-                if (lo <= mB && mB < hi) thr[1] = (double)x[k];
-              }
-              z[k] = __ldg(&a.ztab[lo + hi - 1]);   // r2 - 2 = 2*lo + eq - 1
-            } else z[k] = (T)0;
+            const bool valid = lane + 32 * k < niter;
+            const unsigned cw = CNT[bo[k] & 0xffffu];
+            const unsigned st = cw & 0xffffu, c = valid ? (cw >> 16) : 0u;
+            const Key key = order_key_nonan(x[k]);
+            vhi[k] = FastKeys<T>::TWO ? (unsigned)((unsigned long long)key >> 32) : (unsigned)key;
+            bo[k] = st | (c << 13) | ((st + (bo[k] >> 16)) << 20);   // start | count | own position
+            cm = (int)c > cm ? (int)c : cm;
+            acc[k] = 0;
           }
+          const int rounds = __reduce_max_sync(0xffffffffu, cm);
+          for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+            for (int k = 0; k < FAST_EPT; ++k) {
+              const unsigned st = bo[k] & 0x1fffu, c = (bo[k] >> 13) & 0x7fu, mypos = bo[k] >> 20;
+              const unsigned idx = (unsigned)r < c ? st + (unsigned)r : mypos;
+              const unsigned yhi = Khi[idx];
+              acc[k] += (unsigned)(yhi < vhi[k]) + ((unsigned)((yhi == vhi[k]) & (idx != mypos)) << 16);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k) {
+            const bool valid = lane + 32 * k < niter;
+            const int st = (int)(bo[k] & 0x1fffu), c = (int)((bo[k] >> 13) & 0x7fu);
+            int less = (int)(acc[k] & 0xffffu), eq = 1;
+            if (__any_sync(0xffffffffu, acc[k] >> 16)) {
+              if (acc[k] >> 16) {
+                const Key key = order_key_nonan(x[k]);
+                const unsigned le = resolve_exact<FastKeys<T>::TWO>(Khi, Klo, st, c, vhi[k], (unsigned)key);
+                less = (int)(le & 0xffffu); eq = (int)(le >> 16);
+              }
+            }
+            const int lo = st + less, hi = lo + eq;
+            if (pass == 0 && a.do_tail && valid) {
+              if (lo <= mA && mA < hi) thr[0] = (double)x[k];
+              if (lo <= mB && mB < hi) thr[1] = (double)x[k];
+            }
+            bo[k] = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
+          }
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k) z[k] = (lane + 32 * k < niter) ? __ldg(&a.ztab[bo[k]]) : (T)0;
         }
       } else {
 #pragma unroll
