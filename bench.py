@@ -275,7 +275,8 @@ def gpu_arm(args):
                    "sharding": f"contiguous parameter ranges over {world} rank(s); results gathered to rank 0 (NCCL)",
                    "l2": "input per GPU (%.1f GB) is larger than the 126 MB L2; no flush needed" % (shard * 32000 / 1e9)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "mcd::slab_kernel<double,256>",
+                     "traffic": traffic, "peak_source": peak_src,
+                     "kernel": {1: "mcd::slab_kernel<double,256>", 2: "large-slab pipeline", 3: "mcd::fast_kernel<double>"}.get(ctx.stat("last_path"), "?"),
                      "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": shard * BYTES_PER_PARAM},
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
     }

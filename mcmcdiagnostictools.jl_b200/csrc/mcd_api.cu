@@ -330,7 +330,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   a.maxlag = pg.maxlag; a.relative = pg.relative; a.ess_nan = pg.ess_nan;
   a.rel_ess_max = rel_ess_max_of<T>((long long)g.niter * g.nch);
   a.ess_out = d_ess; a.rhat_out = d_rhat;
-  a.nbuckets = std::min(std::max(next_pow2(2ll * g.n), 2048), 8192);
+  a.nbuckets = 65536;   // fine buckets, 4-bit packed counters
   a.bucket_limit = ctx->bucket_limit;
   const int dtype = sizeof(T) == 8 ? MCD_F64 : MCD_F32;
   if (a.rank_x || a.do_tail) {
@@ -342,8 +342,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   if (rc) return rc;
   a.redo_count = ctx->d_redo; a.redo_list = ctx->d_redo + 1;
   CU(cudaMemsetAsync(ctx->d_redo, 0, sizeof(int), ctx->stream));
-  const size_t big = std::max<size_t>((size_t)FAST_NCH * FAST_ROW * 8, (size_t)(2 * FAST_NCH * FAST_MAXITER + a.nbuckets + 4) * 4);
-  const size_t smem = align_up(big, 16) + 128 + 64 * 8 + 16 * 8 + 4 * 8 + 8 * 4 + (size_t)(pg.maxlag + 9) * sizeof(T) + 64;
+  const size_t smem = fast_smem_bytes<T>(pg.maxlag);
   auto kern = fast_kernel<T>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(a);

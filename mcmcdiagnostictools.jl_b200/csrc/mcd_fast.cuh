@@ -5,20 +5,28 @@
 // One CTA (8 warps) per parameter, ONE WARP PER SPLIT CHAIN, the slab held in registers:
 //   * global -> registers, coalesced, 16 independent loads in flight per thread (the slab is
 //     read from HBM exactly once and never staged);
-//   * rank-normalisation by counting: a monotone linear bucket map (8192 buckets), one
-//     shared-memory atomic per element, a packed {start,count} scan, a scatter of the
-//     order-preserving keys split into 32-bit hi / lo planes (the resolve loop gathers only the
-//     hi plane; lo is touched on the rare hi tie), exact average-tie ranks, z from a table
-//     indexed by the doubled rank;
-//   * the median for the fold is captured from the ranks (no selection pass), the folded
-//     values are ranked by the same code (second pass of the loop), so `:rank` costs one
-//     HBM read;
+//   * rank-normalisation by counting into 65 536 FINE buckets (monotone linear map) whose
+//     populations live in 4-bit packed counters (8 per word, 32 KB): one shared-memory atomic per
+//     element returns its arrival offset; a nibble-sum scan gives a 16-bit prefix per counter
+//     word; an element's sorted position is prefix + nibble-sum of the lower counters of its
+//     word.  With n <= 4096 values ~90 % of the elements are alone in their bucket and are
+//     ranked in O(1) with no key traffic at all; only members of shared buckets scatter their
+//     order-preserving key (32-bit hi / lo planes) and compare against their few bucket mates
+//     (warp-uniform trip count, inactive lanes read a broadcast sentinel).  A hi-plane tie is
+//     settled exactly on (hi, lo) out of line.  Exact average-tie ranks; z from a table indexed
+//     by the doubled rank;
+//   * the median for the fold is captured from the ranks (no selection pass); the folded values
+//     are ranked by the same code (second pass of the loop), so `:rank` costs one HBM read;
 //   * split-chain moments are warp-shuffle reductions on registers;
 //   * direct autocovariance from a padded (conflict-free) shared-memory copy of the centred
 //     chain, register-blocked 8 lags x 8 draws per lane, lazily in batches of 8 lags with
 //     Geyer's truncation deciding after each batch.
-// Slabs that need the general machinery (NaN, infinite range, a bucket over the limit) are
-// appended to a redo list and recomputed by the general slab kernel.
+// Slabs that need the general machinery (NaN, infinite range, a fine bucket holding >= 15
+// values, i.e. heavy ties) are appended to a redo list and recomputed by the general slab kernel.
+//
+// History (profiles/README.md): v0 ranked with 8192 coarse buckets and compare rounds for every
+// element (83 k warp-instructions per parameter, issue-bound in the ranking phases: IPC ~3 there,
+// insensitive to the bucket count and to doubling the resident warps).
 //
 // Reference citations (/root/reference): utils.jl:13-41,148-193; ess_rhat.jl:362-409,488-624.
 #pragma once
@@ -33,6 +41,40 @@ constexpr int FAST_NCH = 8;               // split chains = warps
 constexpr int FAST_MAXITER = 32 * FAST_EPT;  // 512 draws per split chain
 constexpr int FAST_ROW = 616;             // padded centred-chain row (doubles): pad(575) = 610
 constexpr int FAST_TMAX = 576;            // the row is zero-filled on [niter, FAST_TMAX)
+constexpr int FAST_FINE = 65536;          // fine buckets
+constexpr int FAST_WORDS = FAST_FINE / 8; // counter words (8 nibbles each)
+constexpr int FAST_NMAX = FAST_NCH * FAST_MAXITER;  // 4096
+constexpr int FAST_SENT = FAST_NMAX;      // index of the sentinel key (0xffffffff) in Khi
+
+// shared-memory layout (bytes):
+//   [ FC  : FAST_WORDS u32 ][ WP : FAST_WORDS u16 ]     <- aliased by ZC[8][FAST_ROW] doubles
+//   [ Khi : FAST_NMAX + 32 u32 ][ Klo : FAST_NMAX u32 ]
+//   [ small arrays ]
+constexpr int FAST_OFF_WP = FAST_WORDS * 4;
+constexpr int FAST_OFF_KHI = FAST_OFF_WP + FAST_WORDS * 2;
+constexpr int FAST_OFF_KLO = FAST_OFF_KHI + (FAST_NMAX + 32) * 4;
+constexpr int FAST_OFF_SMALL = FAST_OFF_KLO + FAST_NMAX * 4;
+static_assert(FAST_NCH * FAST_ROW * 8 <= FAST_OFF_KHI, "ZC must fit in the counter region");
+template <typename T> static inline size_t fast_smem_bytes(int maxlag) {
+  return (size_t)FAST_OFF_SMALL + 128 + 64 * 8 + 16 * 8 + 4 * 8 + 16 * 4 + (size_t)(maxlag + 9) * sizeof(T) + 64;
+}
+
+// sum of the eight 4-bit fields of w (each <= 15)
+__device__ __forceinline__ unsigned nibsum(unsigned w) {
+  const unsigned t = (w & 0x0f0f0f0fu) + ((w >> 4) & 0x0f0f0f0fu);
+  return (t * 0x01010101u) >> 24;
+}
+// hi / lo words of the order-preserving key of a non-NaN value (see order_key_nonan)
+__device__ __forceinline__ unsigned key_hi(double v) {
+  const int h = __double2hiint(v + 0.0);
+  return (unsigned)(h ^ ((h >> 31) | (int)0x80000000u));
+}
+__device__ __forceinline__ unsigned key_lo(double v) {
+  const double u = v + 0.0;
+  return (unsigned)(__double2loint(u) ^ (__double2hiint(u) >> 31));
+}
+__device__ __forceinline__ unsigned key_hi(float v) { return order_key_nonan(v); }
+__device__ __forceinline__ unsigned key_lo(float v) { return 0u; }
 
 template <typename T> struct FastArgs {
   const T* x;
@@ -47,8 +89,8 @@ template <typename T> struct FastArgs {
   T* ess_out;
   T* rhat_out;
   const T* ztab;        // [2n-1]
-  int nbuckets;         // multiple of 2048
-  int bucket_limit;
+  int nbuckets;         // FAST_FINE
+  int bucket_limit;     // unused (a 4-bit counter caps a bucket at 15)
   int* redo_list;
   int* redo_count;
 };
@@ -115,26 +157,25 @@ template <typename T>
 __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T> a) {
   using Key = typename Traits<T>::Key;
   extern __shared__ __align__(16) unsigned char smem[];
-  const int B = a.nbuckets;
-  // layout: [Khi n*4][Klo n*4][CNT (B+4)*4] aliased by ZC[8][FAST_ROW] doubles ; then small arrays
   const int n = FAST_NCH * a.niter;
-  unsigned* Khi = reinterpret_cast<unsigned*>(smem);
-  unsigned* Klo = Khi + FAST_NCH * FAST_MAXITER;
-  unsigned* CNT = Klo + FAST_NCH * FAST_MAXITER;
+  unsigned* FC = reinterpret_cast<unsigned*>(smem);
+  unsigned short* WP = reinterpret_cast<unsigned short*>(smem + FAST_OFF_WP);
+  unsigned* Khi = reinterpret_cast<unsigned*>(smem + FAST_OFF_KHI);
+  unsigned* Klo = reinterpret_cast<unsigned*>(smem + FAST_OFF_KLO);
   double* ZC = reinterpret_cast<double*>(smem);
-  constexpr int BIG = FAST_NCH * FAST_ROW * 8;  // bytes of ZC
-  const int big_bytes = max(BIG, (2 * FAST_NCH * FAST_MAXITER + B + 4) * 4);
-  unsigned char* small = smem + ((big_bytes + 15) & ~15);
+  unsigned char* small = smem + FAST_OFF_SMALL;
   T* cmean = reinterpret_cast<T*>(small);                  // [8]
   T* cvar = cmean + 8;                                     // [8]
   double* part = reinterpret_cast<double*>(small + 128);   // [8][8]
   double* wred = part + 64;                                // [2][8]
   double* thr = wred + 16;                                 // [4]
-  int* iflag = reinterpret_cast<int*>(thr + 4);            // [8]
-  T* gamma = reinterpret_cast<T*>(iflag + 8);              // [maxlag + 9]
+  int* iflag = reinterpret_cast<int*>(thr + 4);            // [8] warp totals / flags
+  int* woffx = iflag + 8;                                  // [8] exclusive warp offsets
+  T* gamma = reinterpret_cast<T*>(woffx + 8);              // [maxlag + 9]
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int niter = a.niter;
+  if (tid == 0) Khi[FAST_SENT] = 0xffffffffu;   // compares greater than every finite key, equal to none
 
   for (long long param = blockIdx.x; param < a.params; param += gridDim.x) {
     const T* __restrict__ src = a.x + param * (long long)n + w * niter;
@@ -198,7 +239,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
         }
         const bool is_const = !(vmax > vmin);
         const T range = vmax - vmin;
-        const T scale = (T)B / range;
+        const T scale = (T)FAST_FINE / range;
         if (!is_const && (!(range < (T)CUDART_INF) || !(scale > (T)0) || !(scale < (T)CUDART_INF))) { redo = true; break; }
         if (is_const) {
           // every value ties: rank (n+1)/2
@@ -207,32 +248,33 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
           for (int k = 0; k < FAST_EPT; ++k) z[k] = zc;
           if (pass == 0 && tid == 0) { thr[0] = (double)vmin; thr[1] = (double)vmin; }
         } else {
-          // ---- count ---------------------------------------------------------------------------
-          for (int i = tid; i < (B + 4) / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(CNT)[i] = make_uint4(0, 0, 0, 0);
+          // ---- count: 4-bit packed populations, one atomic per element --------------------------
+          for (int i = tid; i < FAST_WORDS / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(FC)[i] = make_uint4(0, 0, 0, 0);
           __syncthreads();
-          unsigned bo[FAST_EPT];
+          unsigned bo[FAST_EPT];   // fine bucket | arrival offset << 16 ; later: packed rank info
           unsigned maxoff = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
             if (lane + 32 * k < niter) {
-              const int b = bucket_of<T>(x[k], (double)vmin, (double)scale, B);
-              const unsigned old = atomicAdd(&CNT[b], 0x10000u) >> 16;
-              maxoff = old > maxoff ? old : maxoff;
-              bo[k] = (unsigned)b | (old << 16);
+              const unsigned fb = (unsigned)bucket_of<T>(x[k], (double)vmin, (double)scale, FAST_FINE);
+              const unsigned sh = (fb & 7u) * 4u;
+              const unsigned off = (atomicAdd(&FC[fb >> 3], 1u << sh) >> sh) & 15u;
+              maxoff = off > maxoff ? off : maxoff;
+              bo[k] = fb | (off << 16);
             } else bo[k] = 0;
           }
-          if (__syncthreads_or(maxoff >= (unsigned)a.bucket_limit)) { redo = true; break; }
-          // ---- scan: CNT[b] = start | count << 16 ---------------------------------------------------
+          // a counter that reaches 16 spills into its neighbour: the value that did it saw 15
+          if (__syncthreads_or(maxoff >= 15u)) { redo = true; break; }
+          // ---- scan: WP[word] = #values in earlier words of this warp's 1024-word range ---------
           {
-            const int per_warp = B / FAST_NCH;       // buckets per warp, multiple of 256
             unsigned carry = 0;
-            // each lane owns 4 buckets in each of two consecutive 128-bucket groups; the two
-            // lane totals ride one 32-bit shuffle scan packed as 16-bit halves (n <= 4096)
-            for (int it = 0; it < per_warp / 256; ++it) {
-              uint4* p4 = reinterpret_cast<uint4*>(CNT + w * per_warp + it * 256) + lane;
-              uint4 c4 = p4[0], d4 = p4[32];
-              const unsigned c0 = c4.x >> 16, c1 = c4.y >> 16, c2 = c4.z >> 16, c3 = c4.w >> 16;
-              const unsigned d0 = d4.x >> 16, d1 = d4.y >> 16, d2 = d4.z >> 16, d3 = d4.w >> 16;
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+              const int wbase = w * 1024 + it * 256 + 4 * lane;
+              const uint4 c4 = *reinterpret_cast<const uint4*>(FC + wbase);
+              const uint4 d4 = *reinterpret_cast<const uint4*>(FC + wbase + 128);
+              const unsigned c0 = nibsum(c4.x), c1 = nibsum(c4.y), c2 = nibsum(c4.z), c3 = nibsum(c4.w);
+              const unsigned d0 = nibsum(d4.x), d1 = nibsum(d4.y), d2 = nibsum(d4.z), d3 = nibsum(d4.w);
               const unsigned tot = (c0 + c1 + c2 + c3) | ((d0 + d1 + d2 + d3) << 16);
               unsigned incl = tot;
 #pragma unroll
@@ -242,86 +284,71 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
               }
               const unsigned all = __shfl_sync(0xffffffffu, incl, 31);
               const unsigned excl = incl - tot;
-              unsigned s0 = carry + (excl & 0xffffu);
-              c4.x = s0 | (c0 << 16); s0 += c0;
-              c4.y = s0 | (c1 << 16); s0 += c1;
-              c4.z = s0 | (c2 << 16); s0 += c2;
-              c4.w = s0 | (c3 << 16);
-              unsigned s1 = carry + (all & 0xffffu) + (excl >> 16);
-              d4.x = s1 | (d0 << 16); s1 += d0;
-              d4.y = s1 | (d1 << 16); s1 += d1;
-              d4.z = s1 | (d2 << 16); s1 += d2;
-              d4.w = s1 | (d3 << 16);
-              p4[0] = c4; p4[32] = d4;
+              const unsigned s0 = carry + (excl & 0xffffu);
+              const unsigned s1 = carry + (all & 0xffffu) + (excl >> 16);
+              uint2 pc, pd;
+              pc.x = s0 | ((s0 + c0) << 16); pc.y = (s0 + c0 + c1) | ((s0 + c0 + c1 + c2) << 16);
+              pd.x = s1 | ((s1 + d0) << 16); pd.y = (s1 + d0 + d1) | ((s1 + d0 + d1 + d2) << 16);
+              *reinterpret_cast<uint2*>(WP + wbase) = pc;
+              *reinterpret_cast<uint2*>(WP + wbase + 128) = pd;
               carry += (all & 0xffffu) + (all >> 16);
             }
             if (lane == 0) iflag[w] = (int)carry;
             __syncthreads();
-            unsigned woff = 0;
-            for (int i = 0; i < w; ++i) woff += (unsigned)iflag[i];
-            if (woff) {
-              for (int it = 0; it < per_warp / 128; ++it) {  // 128 buckets = 32 lanes x uint4
-                uint4* p4 = reinterpret_cast<uint4*>(CNT + w * per_warp + it * 128) + lane;
-                uint4 c4 = *p4;
-                c4.x += woff; c4.y += woff; c4.z += woff; c4.w += woff;
-                *p4 = c4;
-              }
-            }
+            if (tid < FAST_NCH) { int o = 0; for (int i = 0; i < tid; ++i) o += iflag[i]; woffx[tid] = o; }
             __syncthreads();
           }
-          // ---- scatter the keys (hi / lo planes) --------------------------------------------------
+          // ---- position: start of the fine bucket, population, own slot; shared buckets scatter ----
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            if (lane + 32 * k < niter) {
-              const unsigned pos = (CNT[bo[k] & 0xffffu] & 0xffffu) + (bo[k] >> 16);
-              const Key key = order_key_nonan(x[k]);
-              if (FastKeys<T>::TWO) { Khi[pos] = (unsigned)((unsigned long long)key >> 32); Klo[pos] = (unsigned)key; }
-              else Khi[pos] = (unsigned)key;
+            const bool valid = lane + 32 * k < niter;
+            const unsigned fb = bo[k] & 0xffffu, off = bo[k] >> 16;
+            const unsigned word = fb >> 3, sh = (fb & 7u) * 4u;
+            const unsigned fw = FC[word];
+            const unsigned st = (unsigned)WP[word] + (unsigned)woffx[word >> 10] + nibsum(fw & ((1u << sh) - 1u));
+            const unsigned c = valid ? ((fw >> sh) & 15u) : 0u;
+            if (c >= 2u) {
+              Khi[st + off] = key_hi(x[k]);
+              if (FastKeys<T>::TWO) Klo[st + off] = key_lo(x[k]);
             }
+            bo[k] = st | (c << 13);
           }
           __syncthreads();
-          // ---- resolve: exact doubled average rank, z lookup, median capture ------------------------
-          // Round r compares every element with the r-th member of its bucket, for all 16 elements
-          // of the thread at once (16 independent shared-memory gathers in flight).  The trip count
-          // is the warp-wide maximum bucket population; an element past its bucket end re-reads its
-          // own slot, which contributes nothing.  Only the 32-bit hi plane is gathered; a hi tie
-          // with another element (two values within 2^-20 relative) is settled exactly on (hi, lo)
-          // by resolve_exact().
+          // ---- resolve shared buckets (one fused loop: every round compares all 16 elements of the
+          // thread with the r-th member of their buckets; singletons and finished elements read the
+          // broadcast sentinel), finalise ranks, capture the median --------------------------------------
           const int mA = (n & 1) ? n / 2 : n / 2 - 1, mB = n / 2;
           unsigned vhi[FAST_EPT], acc[FAST_EPT];
-          int cm = 0;
+          int cmx = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            const bool valid = lane + 32 * k < niter;
-            const unsigned cw = CNT[bo[k] & 0xffffu];
-            const unsigned st = cw & 0xffffu, c = valid ? (cw >> 16) : 0u;
-            const Key key = order_key_nonan(x[k]);
-            vhi[k] = FastKeys<T>::TWO ? (unsigned)((unsigned long long)key >> 32) : (unsigned)key;
-            bo[k] = st | (c << 13) | ((st + (bo[k] >> 16)) << 20);   // start | count | own position
-            cm = (int)c > cm ? (int)c : cm;
+            const int c = (int)(bo[k] >> 13);
+            cmx = c > cmx ? c : cmx;
+            vhi[k] = key_hi(x[k]);
             acc[k] = 0;
           }
-          const int rounds = __reduce_max_sync(0xffffffffu, cm);
-          for (int r = 0; r < rounds; ++r) {
+          const int trip = __reduce_max_sync(0xffffffffu, cmx >= 2 ? cmx : 0);
+          for (int r = 0; r < trip; ++r) {
 #pragma unroll
             for (int k = 0; k < FAST_EPT; ++k) {
-              const unsigned st = bo[k] & 0x1fffu, c = (bo[k] >> 13) & 0x7fu, mypos = bo[k] >> 20;
-              const unsigned idx = (unsigned)r < c ? st + (unsigned)r : mypos;
-              const unsigned yhi = Khi[idx];
-              acc[k] += (unsigned)(yhi < vhi[k]) + ((unsigned)((yhi == vhi[k]) & (idx != mypos)) << 16);
+              const unsigned st = bo[k] & 0x1fffu, c = bo[k] >> 13;
+              const unsigned ce = c >= 2u ? c : 0u;
+              const unsigned yhi = Khi[(unsigned)r < ce ? st + (unsigned)r : (unsigned)FAST_SENT];
+              acc[k] += (unsigned)(yhi < vhi[k]) + ((unsigned)(yhi == vhi[k]) << 16);
             }
           }
+          unsigned anytie = 0;
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k) anytie |= (acc[k] >> 17);   // eqc >= 2
+          const bool slow = __any_sync(0xffffffffu, anytie != 0);
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
             const bool valid = lane + 32 * k < niter;
-            const int st = (int)(bo[k] & 0x1fffu), c = (int)((bo[k] >> 13) & 0x7fu);
+            const int st = (int)(bo[k] & 0x1fffu), c = (int)(bo[k] >> 13);
             int less = (int)(acc[k] & 0xffffu), eq = 1;
-            if (__any_sync(0xffffffffu, acc[k] >> 16)) {
-              if (acc[k] >> 16) {
-                const Key key = order_key_nonan(x[k]);
-                const unsigned le = resolve_exact<FastKeys<T>::TWO>(Khi, Klo, st, c, vhi[k], (unsigned)key);
-                less = (int)(le & 0xffffu); eq = (int)(le >> 16);
-              }
+            if (slow && (acc[k] >> 17)) {   // another member shares the hi word: exact comparison on (hi, lo)
+              const unsigned le = resolve_exact<FastKeys<T>::TWO>(Khi, Klo, st, c, vhi[k], key_lo(x[k]));
+              less = (int)(le & 0xffffu); eq = (int)(le >> 16);
             }
             const int lo = st + less, hi = lo + eq;
             if (pass == 0 && a.do_tail && valid) {
