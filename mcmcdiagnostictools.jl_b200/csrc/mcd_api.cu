@@ -46,6 +46,7 @@ struct mcd_ctx {
   long long h2d_chunk_bytes = 256ll << 20;
   long long workspace_bytes = 6ll << 30;
   int bucket_limit = 64;
+  int fast_pad_smem = 0;   // developer knob: extra dynamic shared memory (lowers CTAs/SM)
   // stats
   long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   int last_path = 0;
@@ -342,7 +343,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   if (rc) return rc;
   a.redo_count = ctx->d_redo; a.redo_list = ctx->d_redo + 1;
   CU(cudaMemsetAsync(ctx->d_redo, 0, sizeof(int), ctx->stream));
-  const size_t smem = fast_smem_bytes<T>(pg.maxlag);
+  const size_t smem = fast_smem_bytes<T>(pg.maxlag) + (size_t)ctx->fast_pad_smem;
   auto kern = fast_kernel<T>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(a);
@@ -596,6 +597,7 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   if (k == "force_path") { if (value < 0 || value > 3) return fail(ctx, MCD_EINVAL, "force_path in 0..3"); ctx->force_path = (int)value; }
   else if (k == "h2d_chunk_bytes") { if (value < 1) return fail(ctx, MCD_EINVAL, "h2d_chunk_bytes >= 1"); ctx->h2d_chunk_bytes = value; }
   else if (k == "workspace_bytes") { if (value < (1 << 20)) return fail(ctx, MCD_EINVAL, "workspace_bytes >= 1 MiB"); ctx->workspace_bytes = value; }
+  else if (k == "fast_pad_smem") { ctx->fast_pad_smem = (int)value; }
   else if (k == "sort_bucket_limit") { if (value < 0) return fail(ctx, MCD_EINVAL, "sort_bucket_limit >= 0"); ctx->bucket_limit = (int)value; }
   else return fail(ctx, MCD_EINVAL, "unknown option '%s'", key);
   return MCD_OK;
