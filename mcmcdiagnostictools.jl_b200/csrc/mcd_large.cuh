@@ -346,9 +346,121 @@ __global__ void __launch_bounds__(LG_THREADS) fft_chain_kernel(const T* __restri
   for (int t = threadIdx.x; t < N; t += LG_THREADS) { Cx<T> c = f[t]; c.x = c.x * c.x + c.y * c.y; c.y = (T)0; f[t] = c; }
   __syncthreads();
   Cx<T>* r = fft_block<T, LG_THREADS>(f, o, N, tw, true);
-  const T c0 = r[0].x, v = cv[wid];
   T* dst = ac + wid * (long long)(maxlag + 1);
-  for (int k = threadIdx.x; k <= maxlag; k += LG_THREADS) dst[k] = (r[k].x / c0) * v;
+  for (int k = threadIdx.x; k <= maxlag; k += LG_THREADS) dst[k] = r[k].x;   // raw Re c[k]; the ratio is formed later
+}
+
+// ---- four-step FFT for chains whose transform does not fit shared memory ---------------------------
+// N = N1 * N2 (both 2^a 3^b).  With n = N2 n1 + n2 and k = k1 + N1 k2:
+//   X[k1 + N1 k2] = sum_n2 W_N^(n2 k1) [ sum_n1 x[N2 n1 + n2] W_N1^(n1 k1) ] W_N2^(n2 k2)
+// step 1 (cols_fwd): N1-point FFTs down the columns n2 (tiles of TC columns per CTA), times the
+//                    twiddle W_N^(n2 k1), stored row-major B[k1][n2];
+// step 2+3 (rows):   per row k1: N2-point FFT, |.|^2, inverse N2-point FFT, times W_N^(-n2 k1);
+// step 4 (cols_inv): inverse N1-point FFTs down the columns, only for the columns and outputs with
+//                    n = N2 n1 + n2 <= maxlag (the only lags ever read, ess_rhat.jl:181-195).
+// W_N^m is the product of two table entries, m = mh * 1024 + ml.
+template <typename T>
+__device__ __forceinline__ Cx<T> big_twiddle(const Cx<T>* __restrict__ twh, const Cx<T>* __restrict__ twl, long long m, bool conj) {
+  const Cx<T> a = twh[m >> 10], b = twl[m & 1023];
+  Cx<T> r;
+  r.x = a.x * b.x - a.y * b.y;
+  r.y = a.x * b.y + a.y * b.x;
+  if (conj) r.y = -r.y;
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LG_THREADS) fft4_cols_fwd_kernel(const T* __restrict__ Y, SplitGeom g, const T* __restrict__ cm,
+                                                                   int N1, int N2, int TC, const Cx<T>* __restrict__ tw1,
+                                                                   const Cx<T>* __restrict__ twh, const Cx<T>* __restrict__ twl,
+                                                                   Cx<T>* __restrict__ B) {
+  extern __shared__ __align__(16) unsigned char smem_fft[];
+  Cx<T>* buf = reinterpret_cast<Cx<T>*>(smem_fft);          // [TC][2][N1]
+  const int tiles = N2 / TC;
+  const long long wid = blockIdx.x / tiles;                  // chain id within the chunk
+  const int col0 = (int)(blockIdx.x % tiles) * TC;
+  const long long param = wid / g.nch;
+  const int j = (int)(wid % g.nch);
+  const T* p = Y + param * (long long)g.n + g.chain_start(j);
+  const T m = cm[wid];
+  for (int idx = threadIdx.x; idx < N1 * TC; idx += LG_THREADS) {
+    const int n1 = idx / TC, c = idx - n1 * TC;
+    const long long nn = (long long)N2 * n1 + col0 + c;
+    Cx<T> v; v.x = nn < g.niter ? (T)(p[nn] - m) : (T)0; v.y = (T)0;
+    buf[(2 * c) * N1 + n1] = v;
+  }
+  __syncthreads();
+  const long long N = (long long)N1 * N2;
+  Cx<T>* Bc = B + wid * N;
+  for (int c = 0; c < TC; ++c) {
+    Cx<T>* r = fft_block<T, LG_THREADS>(buf + (2 * c) * N1, buf + (2 * c + 1) * N1, N1, tw1, false);
+    for (int k1 = threadIdx.x; k1 < N1; k1 += LG_THREADS) {
+      const Cx<T> w = big_twiddle<T>(twh, twl, (long long)(col0 + c) * k1, false);
+      const Cx<T> u = r[k1];
+      Cx<T> o; o.x = u.x * w.x - u.y * w.y; o.y = u.x * w.y + u.y * w.x;
+      Bc[(long long)k1 * N2 + col0 + c] = o;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LG_THREADS) fft4_rows_kernel(Cx<T>* __restrict__ B, int N1, int N2, const Cx<T>* __restrict__ tw2,
+                                                               const Cx<T>* __restrict__ twh, const Cx<T>* __restrict__ twl) {
+  extern __shared__ __align__(16) unsigned char smem_fft[];
+  Cx<T>* fa = reinterpret_cast<Cx<T>*>(smem_fft);
+  Cx<T>* fb = fa + N2;
+  const long long wid = blockIdx.x / N1;
+  const int k1 = (int)(blockIdx.x % N1);
+  Cx<T>* row = B + wid * (long long)N1 * N2 + (long long)k1 * N2;
+  for (int t = threadIdx.x; t < N2; t += LG_THREADS) fa[t] = row[t];
+  __syncthreads();
+  Cx<T>* f = fft_block<T, LG_THREADS>(fa, fb, N2, tw2, false);
+  Cx<T>* o = (f == fa) ? fb : fa;
+  for (int t = threadIdx.x; t < N2; t += LG_THREADS) { Cx<T> c = f[t]; c.x = c.x * c.x + c.y * c.y; c.y = (T)0; f[t] = c; }
+  __syncthreads();
+  Cx<T>* r = fft_block<T, LG_THREADS>(f, o, N2, tw2, true);
+  for (int n2 = threadIdx.x; n2 < N2; n2 += LG_THREADS) {
+    const Cx<T> w = big_twiddle<T>(twh, twl, (long long)n2 * k1, true);
+    const Cx<T> u = r[n2];
+    Cx<T> v; v.x = u.x * w.x - u.y * w.y; v.y = u.x * w.y + u.y * w.x;
+    row[n2] = v;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LG_THREADS) fft4_cols_inv_kernel(const Cx<T>* __restrict__ D, int N1, int N2, int TC,
+                                                                   const Cx<T>* __restrict__ tw1, int maxlag, int tiles,
+                                                                   T* __restrict__ ac) {
+  extern __shared__ __align__(16) unsigned char smem_fft[];
+  Cx<T>* buf = reinterpret_cast<Cx<T>*>(smem_fft);          // [TC][2][N1]
+  const long long wid = blockIdx.x / tiles;
+  const int col0 = (int)(blockIdx.x % tiles) * TC;
+  const Cx<T>* Dc = D + wid * (long long)N1 * N2;
+  for (int idx = threadIdx.x; idx < N1 * TC; idx += LG_THREADS) {
+    const int k1 = idx / TC, c = idx - k1 * TC;
+    buf[(2 * c) * N1 + k1] = Dc[(long long)k1 * N2 + col0 + c];
+  }
+  __syncthreads();
+  T* dst = ac + wid * (long long)(maxlag + 1);
+  for (int c = 0; c < TC; ++c) {
+    Cx<T>* r = fft_block<T, LG_THREADS>(buf + (2 * c) * N1, buf + (2 * c + 1) * N1, N1, tw1, true);
+    for (int n1 = threadIdx.x; n1 < N1; n1 += LG_THREADS) {
+      const long long nn = (long long)N2 * n1 + col0 + c;
+      if (nn <= maxlag) dst[nn] = r[n1].x;
+    }
+  }
+}
+
+// exp(-2 pi i j stride / N) for j < count
+template <typename T> __global__ void twiddle_stride_kernel(Cx<T>* tw, long long N, long long stride, int count) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) {
+    double s, c;
+    const long long m = ((long long)k * stride) % N;
+    sincospi(-2.0 * (double)m / (double)N, &s, &c);
+    Cx<T> w; w.x = (T)c; w.y = (T)s;
+    tw[k] = w;
+  }
 }
 
 // ---- R-hat / ESS per parameter -----------------------------------------------------------------------
@@ -394,7 +506,11 @@ __global__ void __launch_bounds__(LG_THREADS) ess_kernel(const EssArgs<T> a) {
     const T unc = (T)(niter - 1) / (T)niter;
     for (int k = threadIdx.x; k <= maxlag; k += LG_THREADS) {
       double s = 0.0;
-      for (int j = 0; j < g.nch; ++j) s += (double)ac[(long long)j * (maxlag + 1) + k];
+      // mean_i( Re c[k,i] / Re c[0,i] * var_i ) * (niter-1)/niter   (ess_rhat.jl:181-195)
+      for (int j = 0; j < g.nch; ++j) {
+        const T* aj = ac + (long long)j * (maxlag + 1);
+        s += (double)((aj[k] / aj[0]) * cv[j]);
+      }
       gamma[k] = (T)(s / (double)g.nch) * unc;
     }
     __syncthreads();
@@ -592,10 +708,27 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   needs_sort |= combine == CB_MCSE_QUANTILE;
   const bool use_fft = any_ess && method == 1 && !ess_nan;
   const long long fftN = use_fft ? nextprod23_l(2ll * g.niter - 1) : 0;
-  if (use_fft && (size_t)fftN * 4 * ts > (size_t)env.smem_optin) {
-    msg = "FFTAutocovMethod with FFT length " + std::to_string(fftN) +
-          " exceeds the shared-memory FFT of this build (four-step FFT not built yet)";
-    return -4;
+  // FFT plan: one CTA per chain while two N-point complex buffers fit shared memory, else four-step
+  const bool fft_big = use_fft && (size_t)fftN * 4 * ts > (size_t)env.smem_optin - 1024;
+  long long fN1 = 0, fN2 = 0;
+  int fTC = 1;
+  if (fft_big) {
+    const long long cap2 = ((long long)env.smem_optin - 1024) / (long long)(4 * ts);   // row FFT: 2 buffers of N2
+    long long best = 0;
+    for (long long a3 = 1; a3 <= fftN; a3 *= 3) {
+      if (fftN % a3) break;
+      for (long long f = a3; f <= fftN; f *= 2) {
+        if (fftN % f) break;
+        const long long other = fftN / f;
+        if (f > other || other > cap2 || (fftN >> 10) + 1 > (1ll << 31)) continue;
+        if (f > best) best = f;
+      }
+    }
+    if (best == 0) { msg = "FFTAutocovMethod: FFT length " + std::to_string(fftN) + " is beyond the four-step plan of this build"; return -4; }
+    fN1 = best; fN2 = fftN / best;
+    const long long capc = ((long long)env.smem_optin - 1024) / (long long)(4 * ts * fN1);  // column tiles: TC * 2 buffers of N1
+    for (int tc : {4, 3, 2, 1}) if (tc <= capc && fN2 % tc == 0) { fTC = tc; break; }
+    if (capc < 1) { msg = "FFTAutocovMethod: column FFT does not fit shared memory"; return -4; }
   }
   const long long nan_tiles = (n + NAN_TILE - 1) / NAN_TILE;
   const long long gam_stride = maxlag + 1 + LAG_BATCH;
@@ -608,6 +741,7 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   per += 2 * al((size_t)g.nch * ts);
   if (any_ess) per += al((size_t)gam_stride * ts);
   if (use_fft) per += al((size_t)g.nch * (maxlag + 1) * ts);
+  if (fft_big) per += al((size_t)g.nch * fftN * 2 * ts);
   if (any_nested) per += al((size_t)2 * nsuper * 8);
   per += 256 * 2;  // thresholds, nnan, results (per-param scalars; generous)
   long long chunk = std::max<long long>(1, env.workspace_bytes / (long long)per);
@@ -615,7 +749,8 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   // grid limits: blocks = chunk * tiles must stay below 2^31
   const long long sort_tiles = (n + SORT_TILE - 1) / SORT_TILE, merge_tiles = (n + MERGE_TILE - 1) / MERGE_TILE;
   const long long max_tiles = std::max<long long>(std::max(sort_tiles, merge_tiles), std::max<long long>(nan_tiles, g.nch));
-  chunk = std::max<long long>(1, std::min(chunk, ((1ll << 31) - 1) / max_tiles));
+  const long long fft_tiles = fft_big ? (long long)g.nch * std::max(fN1, fN2 / fTC) : 0;
+  chunk = std::max<long long>(1, std::min(chunk, ((1ll << 31) - 1) / std::max(max_tiles, fft_tiles)));
 
   const size_t scal = al((size_t)chunk * 8);
   size_t need = 0;
@@ -629,7 +764,8 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   const size_t oGAM = carve(any_ess ? (size_t)chunk * gam_stride * ts : 0);
   const size_t oAC = carve(use_fft ? (size_t)chunk * g.nch * (maxlag + 1) * ts : 0);
   const size_t oNS = carve(any_nested ? (size_t)chunk * 2 * nsuper * 8 : 0);
-  const size_t oTW = carve(use_fft ? (size_t)fftN * 2 * ts : 0);
+  const size_t oTW = carve(use_fft ? (size_t)(fft_big ? (fN1 + fN2 + (fftN >> 10) + 1 + 1024) : fftN) * 2 * ts : 0);
+  const size_t oFB = carve(fft_big ? (size_t)chunk * g.nch * fftN * 2 * ts : 0);
   const size_t oTHR = carve(scal), oTHR2 = carve(scal), oEX0 = carve(scal), oEX1 = carve(scal);
   const size_t oNNX = carve(scal), oNNY = carve(scal);
   size_t oRE[MAX_STEPS], oRR[MAX_STEPS];
@@ -651,6 +787,8 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   T* ac = (T*)(wb + oAC);
   double* nscr = (double*)(wb + oNS);
   Cx<T>* tw = (Cx<T>*)(wb + oTW);
+  Cx<T>* fB = (Cx<T>*)(wb + oFB);
+  Cx<T>* tw1 = tw; Cx<T>* tw2 = tw + fN1; Cx<T>* twh = tw2 + fN2; Cx<T>* twl = twh + (fftN >> 10) + 1;
   double* thr = (double*)(wb + oTHR);
   double* thr2 = (double*)(wb + oTHR2);
   double* ex0 = (double*)(wb + oEX0);
@@ -659,10 +797,20 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   int* nnY = (int*)(wb + oNNY);
   cudaStream_t st = env.stream;
 
-  if (use_fft) {
+  if (use_fft && !fft_big) {
     twiddle_kernel_l<T><<<(unsigned)((fftN + 255) / 256), 256, 0, st>>>(tw, (int)fftN);
     LAUNCHED();
     LCU(cudaFuncSetAttribute(fft_chain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fftN * 4 * ts)));
+  }
+  if (fft_big) {
+    twiddle_stride_kernel<T><<<(unsigned)((fN1 + 255) / 256), 256, 0, st>>>(tw1, fN1, 1, (int)fN1); LAUNCHED();
+    twiddle_stride_kernel<T><<<(unsigned)((fN2 + 255) / 256), 256, 0, st>>>(tw2, fN2, 1, (int)fN2); LAUNCHED();
+    const int nh = (int)((fftN >> 10) + 1);
+    twiddle_stride_kernel<T><<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(twh, fftN, 1024, nh); LAUNCHED();
+    twiddle_stride_kernel<T><<<4, 256, 0, st>>>(twl, fftN, 1, 1024); LAUNCHED();
+    LCU(cudaFuncSetAttribute(fft4_cols_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fTC * fN1 * 4 * ts)));
+    LCU(cudaFuncSetAttribute(fft4_cols_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fTC * fN1 * 4 * ts)));
+    LCU(cudaFuncSetAttribute(fft4_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fN2 * 4 * ts)));
   }
   const T rel_ess_max = (T)env.rel_ess_max;
   const int ew_blocks_cap = env.sm_count * 16;
@@ -778,8 +926,21 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
           LAUNCHED();
         } else {
           const bool want_ess = stp.reduce == RD_ESS_RHAT;
-          if (want_ess && use_fft) {
+          if (want_ess && use_fft && !fft_big) {
             fft_chain_kernel<T><<<(unsigned)nwork, LG_THREADS, (size_t)fftN * 4 * ts, st>>>(proxy, g, cm, cv, (int)fftN, tw, maxlag, ac);
+            LAUNCHED();
+          }
+          if (want_ess && fft_big) {
+            const int tiles_f = (int)(fN2 / fTC);
+            fft4_cols_fwd_kernel<T><<<(unsigned)(nwork * tiles_f), LG_THREADS, (size_t)fTC * fN1 * 4 * ts, st>>>(
+                proxy, g, cm, (int)fN1, (int)fN2, fTC, tw1, twh, twl, fB);
+            LAUNCHED();
+            fft4_rows_kernel<T><<<(unsigned)(nwork * fN1), LG_THREADS, (size_t)fN2 * 4 * ts, st>>>(fB, (int)fN1, (int)fN2, tw2, twh, twl);
+            LAUNCHED();
+            const long long ncols = std::min<long long>(fN2, (long long)maxlag + 1);
+            const int tiles_i = (int)((ncols + fTC - 1) / fTC);
+            fft4_cols_inv_kernel<T><<<(unsigned)(nwork * tiles_i), LG_THREADS, (size_t)fTC * fN1 * 4 * ts, st>>>(
+                fB, (int)fN1, (int)fN2, fTC, tw1, maxlag, tiles_i, ac);
             LAUNCHED();
           }
           EssArgs<T> ea;

@@ -130,3 +130,24 @@ def test_auto_path_picks_large_for_big_slabs(o):
     assert ctx.stat("last_path") == 2
     So, Ro = o.ess_rhat(x)
     assert close(S, So, RTOL64) and close(R, Ro, RTOL64)
+
+
+@pytest.mark.parametrize("draws,chains,split", [(8000, 2, 2), (10000, 2, 2), (9001, 3, 1), (30000, 1, 2)])
+def test_large_four_step_fft(o, draws, chains, split):
+    """FFTAutocovMethod on chains whose transform (nextprod([2,3], 2 niter - 1) points) does not fit
+    shared memory: four-step FFT (8192 = 2^13, 10368 = 2^7 3^4, 18432 = 2^11 3^2, 32768 points)."""
+    import mcmcdiag_b200 as m
+    x = o.ar1(0.8, np.sqrt(1 - 0.64), draws, chains, 3, rng=rng(40))
+    for kind in ("basic", "bulk"):
+        S, R = m.ess_rhat(x, kind=kind, split_chains=split, autocov_method=m.FFTAutocovMethod())
+        assert m.get_context(0).stat("last_path") == 2
+        So, Ro = o.ess_rhat(x, kind=kind, split_chains=split, autocov_method=o.FFTAutocovMethod())
+        assert close(S, So, RTOL64), (S, So)
+        assert close(R, Ro, RTOL64)
+        Sd, _ = m.ess_rhat(x, kind=kind, split_chains=split)
+        assert close(S, Sd, 1e-8)                     # FFT ~ direct (test/ess_rhat.jl:228-230)
+    S = m.ess(x, kind="basic", split_chains=split, autocov_method=m.FFTAutocovMethod(), maxlag=5000)
+    assert close(S, o.ess(x, kind="basic", split_chains=split, autocov_method=o.FFTAutocovMethod(), maxlag=5000), RTOL64)
+    x32 = x.astype(np.float32)
+    S32 = m.ess(x32, kind="basic", split_chains=split, autocov_method=m.FFTAutocovMethod())
+    assert close(S32, o.ess(x32, kind="basic", split_chains=split, autocov_method=o.FFTAutocovMethod()), 2e-3)
