@@ -6,6 +6,7 @@
 #include "mcd_common.cuh"
 #include "mcd_slab.cuh"
 #include "mcd_fast.cuh"
+#include "mcd_fastgen.cuh"
 #include "mcd_large.cuh"
 
 #include <algorithm>
@@ -316,6 +317,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   if (ess_live && pg.method != MCD_AUTOCOV_DIRECT) return MCD_OK;
   FastArgs<T> a;
   memset(&a, 0, sizeof a);
+  bool lean = true;
   const Step& s0 = pg.steps[0];
   if (pg.nsteps == 1 && pg.combine == CB_PLAIN && (s0.transform == TR_NONE || s0.transform == TR_RANKNORM) &&
       (s0.reduce == RD_ESS_RHAT || s0.reduce == RD_RHAT)) {
@@ -326,27 +328,97 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
              (s0.reduce == RD_ESS_RHAT || s0.reduce == RD_RHAT) && pg.steps[1].transform == TR_FOLD_RANKNORM &&
              pg.steps[1].reduce == RD_RHAT) {
     a.do_bulk = 1; a.rank_x = 1; a.want_ess = s0.reduce == RD_ESS_RHAT; a.do_tail = 1;
+  } else lean = false;
+  FastGenArgs<T> ga;
+  memset(&ga, 0, sizeof ga);
+  if (!lean) {
+  FastGenArgs<T>& a = ga;
+  const int n = g.n;
+  const int mA = (n & 1) ? n / 2 : n / 2 - 1, mB = n / 2;
+  a.cap_pos[0] = mA; a.cap_pos[1] = mB;
+  // type-7 quantile position and weight (Statistics.quantile, call site src/ess_rhat.jl:655)
+  auto quantile_plan = [&](double p, int f32, int slot, int thr_index) {
+    long long j; double gq;
+    if (f32) {
+      const float pf = (float)p, mm = (float)(1.0 - (double)pf);
+      const float aleph = std::fmaf((float)n, pf, mm);
+      j = (long long)std::trunc(aleph);
+      j = std::min<long long>(std::max<long long>(j, 1), n - 1);
+      float gf = aleph - (float)j;
+      gf = gf < 0.f ? 0.f : (gf > 1.f ? 1.f : gf);
+      gq = (double)gf;
+    } else {
+      const double aleph = std::fma((double)n, p, 1.0 - p);
+      j = (long long)std::trunc(aleph);
+      j = std::min<long long>(std::max<long long>(j, 1), n - 1);
+      gq = aleph - (double)j;
+      gq = gq < 0.0 ? 0.0 : (gq > 1.0 ? 1.0 : gq);
+    }
+    a.cap_pos[slot] = (int)(j - 1); a.cap_pos[slot + 1] = (int)j;
+    a.thr[thr_index].quantile = 1; a.thr[thr_index].capA = slot; a.thr[thr_index].capB = slot + 1;
+    a.thr[thr_index].f32 = f32; a.thr[thr_index].g = gq;
+  };
+  auto ind_red = [&](int i, int thr_index) { a.p0_red[i].src = FS_IND; a.p0_red[i].want_ess = 1; a.p0_red[i].thr = thr_index; };
+  const bool plain1 = pg.nsteps == 1 && pg.combine == CB_PLAIN;
+  if (plain1 && (s0.transform == TR_NONE || s0.transform == TR_RANKNORM) && (s0.reduce == RD_ESS_RHAT || s0.reduce == RD_RHAT)) {
+    a.p0_rank = s0.transform == TR_RANKNORM; a.p0_nred = 1;
+    a.p0_red[0].src = a.p0_rank ? FS_RANKZ : FS_X; a.p0_red[0].want_ess = s0.reduce == RD_ESS_RHAT;
+    a.ess_mode = a.p0_red[0].want_ess; a.rhat_mode = 1;
+  } else if (plain1 && s0.transform == TR_FOLD_RANKNORM && s0.reduce == RD_RHAT) {
+    a.p0_rank = 1; a.ncap = 2; a.do_fold = 1; a.p1_red.src = FS_RANKZ; a.rhat_mode = 2;
+  } else if (pg.nsteps == 2 && pg.combine == CB_RANK && s0.transform == TR_RANKNORM &&
+             (s0.reduce == RD_ESS_RHAT || s0.reduce == RD_RHAT) && pg.steps[1].transform == TR_FOLD_RANKNORM &&
+             pg.steps[1].reduce == RD_RHAT) {
+    a.p0_rank = 1; a.ncap = 2; a.p0_nred = 1; a.p0_red[0].src = FS_RANKZ; a.p0_red[0].want_ess = s0.reduce == RD_ESS_RHAT;
+    a.do_fold = 1; a.p1_red.src = FS_RANKZ; a.ess_mode = a.p0_red[0].want_ess; a.rhat_mode = 3;
+  } else if ((pg.combine == CB_TAIL && pg.nsteps == 3) || (pg.combine == CB_TAIL_ESS && pg.nsteps == 2)) {
+    // _ess(Val(:tail)): min of the two quantile-indicator ESS (src/ess_rhat.jl:301-311) [+ tail R-hat]
+    if (s0.transform != TR_IND_QUANTILE || pg.steps[1].transform != TR_IND_QUANTILE) return MCD_OK;
+    a.p0_rank = 1; a.ncap = 6; a.nthr = 2; a.p0_nred = 2;
+    quantile_plan(s0.p, s0.p_f32, 2, 0); quantile_plan(pg.steps[1].p, pg.steps[1].p_f32, 4, 1);
+    ind_red(0, 0); ind_red(1, 1);
+    a.ess_mode = 2;
+    if (pg.combine == CB_TAIL) {
+      if (pg.steps[2].transform != TR_FOLD_RANKNORM || pg.steps[2].reduce != RD_RHAT) return MCD_OK;
+      a.do_fold = 1; a.p1_red.src = FS_RANKZ; a.rhat_mode = 2;
+    }
+  } else if (plain1 && s0.reduce == RD_ESS_RHAT && !pg.want_rhat && s0.transform == TR_IND_MEDIAN) {
+    a.p0_rank = 1; a.ncap = 2; a.nthr = 1; a.thr[0].quantile = 0; a.thr[0].capA = 0; a.thr[0].capB = 1;
+    a.p0_nred = 1; ind_red(0, 0); a.ess_mode = 1;
+  } else if (plain1 && s0.reduce == RD_ESS_RHAT && !pg.want_rhat && s0.transform == TR_IND_QUANTILE) {
+    a.p0_rank = 1; a.ncap = 4; a.nthr = 1; quantile_plan(s0.p, s0.p_f32, 2, 0);
+    a.p0_nred = 1; ind_red(0, 0); a.ess_mode = 1;
+  } else if (plain1 && s0.reduce == RD_ESS_RHAT && !pg.want_rhat && s0.transform == TR_STDPROXY) {
+    a.p0_nred = 1; a.p0_red[0].src = FS_SQDEV; a.p0_red[0].want_ess = 1; a.ess_mode = 1;
+  } else if (plain1 && s0.reduce == RD_ESS_RHAT && !pg.want_rhat && s0.transform == TR_FOLD_IND_MEDIAN) {
+    a.p0_rank = 1; a.ncap = 2; a.do_fold = 1; a.p1_red.src = FS_IND; a.p1_red.want_ess = 1; a.ess_mode = 4;
   } else return MCD_OK;
-  a.x = dx; a.params = params; a.niter = g.niter;
-  a.maxlag = pg.maxlag; a.relative = pg.relative; a.ess_nan = pg.ess_nan;
-  a.rel_ess_max = rel_ess_max_of<T>((long long)g.niter * g.nch);
-  a.ess_out = d_ess; a.rhat_out = d_rhat;
-  a.nbuckets = 65536;   // fine buckets, 4-bit packed counters
-  a.bucket_limit = ctx->bucket_limit;
+  }
+  a.x = ga.x = dx; a.params = ga.params = params; a.niter = ga.niter = g.niter;
+  a.maxlag = ga.maxlag = pg.maxlag; a.relative = ga.relative = pg.relative; a.ess_nan = ga.ess_nan = pg.ess_nan;
+  a.rel_ess_max = ga.rel_ess_max = rel_ess_max_of<T>((long long)g.niter * g.nch);
+  a.ess_out = ga.ess_out = d_ess; a.rhat_out = ga.rhat_out = d_rhat;
   const int dtype = sizeof(T) == 8 ? MCD_F64 : MCD_F32;
-  if (a.rank_x || a.do_tail) {
+  if (lean ? (a.rank_x || a.do_tail) : (ga.p0_rank || ga.do_fold)) {
     int rc = ensure_ztab(ctx, dtype, g.n);
     if (rc) return rc;
-    a.ztab = (const T*)ctx->ztab;
+    a.ztab = ga.ztab = (const T*)ctx->ztab;
   }
   int rc = ensure_cap(ctx, (void**)&ctx->d_redo, &ctx->redo_cap, (size_t)(params + 1) * sizeof(int));
   if (rc) return rc;
-  a.redo_count = ctx->d_redo; a.redo_list = ctx->d_redo + 1;
+  a.redo_count = ga.redo_count = ctx->d_redo; a.redo_list = ga.redo_list = ctx->d_redo + 1;
   CU(cudaMemsetAsync(ctx->d_redo, 0, sizeof(int), ctx->stream));
-  const size_t smem = fast_smem_bytes<T>(pg.maxlag) + (size_t)ctx->fast_pad_smem;
-  auto kern = fast_kernel<T>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(a);
+  if (lean) {
+    const size_t smem = fast_smem_bytes<T>(pg.maxlag) + (size_t)ctx->fast_pad_smem;
+    auto kern = fast_kernel<T>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(a);
+  } else {
+    const size_t smem = fast_smem_bytes<T>(pg.maxlag) + 16 * 8 + (size_t)ctx->fast_pad_smem;
+    auto kern = fastgen_kernel<T>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(ga);
+  }
   ctx->launches++;
   CU(cudaGetLastError());
   // slabs the fast kernel declined (NaN, infinite range, heavy ties): general slab kernel

@@ -1,0 +1,437 @@
+// mcd_fastgen.cuh — the general form of the fast kernel (mcd_fast.cuh): same shapes (8 split chains
+// of <= 512 draws, direct autocovariance), same register-resident ranking, but a small program of
+// REDUCTIONS per pass, so that the kinds whose proxies are order-statistic indicators reuse the
+// ranks instead of re-sorting:
+//   ess_rhat / ess (kind = :tail)   min of the two quantile-indicator ESS  (src/ess_rhat.jl:301-311)
+//                                   [+ tail R-hat from the folded pass]
+//   ess(kind = median | quantile(p)) indicator x <= threshold              (:630-639, :647-659)
+//   ess(kind = std)                  (x - mean)^2                          (:640-642)
+//   ess(kind = mad)                  fold, then indicator f <= median(f)   (:643-646)
+// The order statistics behind the thresholds (median, type-7 quantile neighbours) are captured
+// while the ranks are at hand; thresholds are then formed exactly as the reference does and the
+// indicator compares the values themselves against them.
+// The headline programs (rank / bulk / basic / tail R-hat) stay on the leaner mcd_fast.cuh kernel.
+#pragma once
+#include "mcd_fast.cuh"
+
+namespace mcd {
+
+// What a reduction (moments [+ autocovariance + Geyer]) runs on
+enum FastSrc : int {
+  FS_X = 0,      // the values themselves                                  (kind basic / estimator mean)
+  FS_RANKZ = 1,  // z of the ranks just computed (must be the first reduction of its pass)
+  FS_IND = 2,    // indicator  value <= threshold                          (median / quantile / tail ESS, mad)
+  FS_SQDEV = 3   // (x - mean over draws and chains)^2                     (estimator std)
+};
+struct FastRed { int src, want_ess, thr; };
+// threshold from captured order statistics: median a/2 + b/2, or type-7 quantile a + g (b - a)
+struct FastThr { int quantile, capA, capB, f32; double g; };
+
+template <typename T> struct FastGenArgs {
+  const T* x;
+  long long params;
+  int niter;            // draws per split chain; n = 8 * niter
+  // pass 0 works on x, pass 1 (do_fold) on |x - median(x)|
+  int p0_rank;          // pass 0 needs the ranks of x (for z, or for order statistics)
+  int p0_nred;          // reductions on pass-0 data -> result slots 0..2
+  FastRed p0_red[3];
+  int ncap;             // order statistics of x to capture: sorted positions (0-based) -> cap[0..ncap)
+  int cap_pos[6];       // when do_fold: cap_pos[0], cap_pos[1] must be the two median positions
+  int nthr;             // thresholds computed from the captures -> thrv[0..nthr)
+  FastThr thr[3];
+  int do_fold;
+  FastRed p1_red;       // reduction on the folded data -> result slot 3 (FS_IND uses the median of the folded values)
+  int ess_mode;         // 0 none, 1 slot 0, 2 min(slot 0, slot 1), 4 slot 3
+  int rhat_mode;        // 0 none, 1 slot 0, 2 slot 3, 3 max(slot 3, slot 0)
+  int maxlag, relative, ess_nan;
+  T rel_ess_max;
+  T* ess_out;
+  T* rhat_out;
+  const T* ztab;        // [2n-1]
+  int* redo_list;
+  int* redo_count;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenArgs<T> a) {
+  using Key = typename Traits<T>::Key;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int n = FAST_NCH * a.niter;
+  unsigned* FC = reinterpret_cast<unsigned*>(smem);
+  unsigned short* WP = reinterpret_cast<unsigned short*>(smem + FAST_OFF_WP);
+  unsigned* Khi = reinterpret_cast<unsigned*>(smem + FAST_OFF_KHI);
+  unsigned* Klo = reinterpret_cast<unsigned*>(smem + FAST_OFF_KLO);
+  double* ZC = reinterpret_cast<double*>(smem);
+  unsigned char* small = smem + FAST_OFF_SMALL;
+  T* cmean = reinterpret_cast<T*>(small);                  // [8]
+  T* cvar = cmean + 8;                                     // [8]
+  double* part = reinterpret_cast<double*>(small + 128);   // [8][8]
+  double* wred = part + 64;                                // [2][8]
+  double* cap = wred + 16;                                 // [8] captured order statistics (6,7: folded median)
+  double* thrv = cap + 8;                                  // [4] thresholds (3: median of the folded values)
+  double* res = thrv + 4;                                  // [8] ess[4], rhat[4] per result slot
+  int* iflag = reinterpret_cast<int*>(res + 8);            // [8] warp totals / flags
+  int* woffx = iflag + 8;                                  // [8] exclusive warp offsets
+  T* gamma = reinterpret_cast<T*>(woffx + 8);              // [maxlag + 9]
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int niter = a.niter;
+  if (tid == 0) Khi[FAST_SENT] = 0xffffffffu;   // compares greater than every finite key, equal to none
+
+  for (long long param = blockIdx.x; param < a.params; param += gridDim.x) {
+    const T* __restrict__ src = a.x + param * (long long)n + w * niter;
+    T x[FAST_EPT], z[FAST_EPT];
+#pragma unroll
+    for (int k = 0; k < FAST_EPT; ++k) {
+      const int t = lane + 32 * k;
+      x[k] = t < niter ? __ldg(&src[t]) : (T)0;
+    }
+    bool redo = false;
+    T vmin = (T)0, vmax = (T)0;
+
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1 && !a.do_fold) break;
+      const bool need_rank = pass == 1 || a.p0_rank;
+      const int nred = pass == 0 ? a.p0_nred : 1;
+      if (pass == 0 && !need_rank && nred == 0) continue;
+      if (pass == 1) {
+        __syncthreads();  // cap[] written by the pass-0 resolve is visible
+        // _fold_around_median: Statistics.median = middle of the two central order statistics
+        const T med = (n & 1) ? (T)cap[0] : (T)((T)cap[0] / (T)2 + (T)cap[1] / (T)2);
+        // |x - med| is monotone on each side of med, so its maximum sits at an extreme of x
+        const T fa = fabs(vmin - med), fb = fabs(vmax - med);
+        vmax = fa > fb ? fa : fb;
+        vmin = (T)0;
+#pragma unroll
+        for (int k = 0; k < FAST_EPT; ++k) x[k] = fabs(x[k] - med);
+      }
+      const bool first_is_rankz = (pass == 0 ? (nred > 0 && a.p0_red[0].src == FS_RANKZ) : a.p1_red.src == FS_RANKZ);
+      if (need_rank) {
+        __syncthreads();  // previous users of the big region (ZC / K / CNT) are done
+        if (pass == 0) {
+          T lmin = (T)CUDART_INF, lmax = -(T)CUDART_INF;
+          int bad = 0;
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k) {
+            if (lane + 32 * k < niter) {
+              const T v = x[k];
+              bad |= (v != v);
+              lmin = v < lmin ? v : lmin;
+              lmax = v > lmax ? v : lmax;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const T p = __shfl_xor_sync(0xffffffffu, lmin, o); lmin = p < lmin ? p : lmin;
+            const T q = __shfl_xor_sync(0xffffffffu, lmax, o); lmax = q > lmax ? q : lmax;
+          }
+          bad = __any_sync(0xffffffffu, bad);
+          if (lane == 0) { wred[w] = (double)lmin; wred[8 + w] = (double)lmax; iflag[w] = bad; }
+          __syncthreads();
+          vmin = (T)wred[0]; vmax = (T)wred[8];
+          int anybad = iflag[0];
+#pragma unroll
+          for (int i = 1; i < FAST_NCH; ++i) {
+            const T p = (T)wred[i], q = (T)wred[8 + i];
+            vmin = p < vmin ? p : vmin; vmax = q > vmax ? q : vmax;
+            anybad |= iflag[i];
+          }
+          if (anybad) { redo = true; break; }
+        }
+        const bool is_const = !(vmax > vmin);
+        const T range = vmax - vmin;
+        const T scale = (T)FAST_FINE / range;
+        if (!is_const && (!(range < (T)CUDART_INF) || !(scale > (T)0) || !(scale < (T)CUDART_INF))) { redo = true; break; }
+        if (is_const) {
+          // every value ties: rank (n+1)/2
+          const T zc = __ldg(&a.ztab[n - 1]);
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k) z[k] = zc;
+          if (tid < 8) cap[tid] = (double)vmin;   // every order statistic equals the common value
+        } else {
+          // ---- count: 4-bit packed populations, one atomic per element --------------------------
+          for (int i = tid; i < FAST_WORDS / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(FC)[i] = make_uint4(0, 0, 0, 0);
+          __syncthreads();
+          unsigned bo[FAST_EPT];   // fine bucket | arrival offset << 16 ; later: packed rank info
+          unsigned maxoff = 0;
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k) {
+            if (lane + 32 * k < niter) {
+              const unsigned fb = (unsigned)bucket_of<T>(x[k], (double)vmin, (double)scale, FAST_FINE);
+              const unsigned sh = (fb & 7u) * 4u;
+              const unsigned off = (atomicAdd(&FC[fb >> 3], 1u << sh) >> sh) & 15u;
+              maxoff = off > maxoff ? off : maxoff;
+              bo[k] = fb | (off << 16);
+            } else bo[k] = 0;
+          }
+          // a counter that reaches 16 spills into its neighbour: the value that did it saw 15
+          if (__syncthreads_or(maxoff >= 15u)) { redo = true; break; }
+          // ---- scan: WP[word] = #values in earlier words of this warp's 1024-word range ---------
+          {
+            unsigned carry = 0;
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+              const int wbase = w * 1024 + it * 256 + 4 * lane;
+              const uint4 c4 = *reinterpret_cast<const uint4*>(FC + wbase);
+              const uint4 d4 = *reinterpret_cast<const uint4*>(FC + wbase + 128);
+              const unsigned c0 = nibsum(c4.x), c1 = nibsum(c4.y), c2 = nibsum(c4.z), c3 = nibsum(c4.w);
+              const unsigned d0 = nibsum(d4.x), d1 = nibsum(d4.y), d2 = nibsum(d4.z), d3 = nibsum(d4.w);
+              const unsigned tot = (c0 + c1 + c2 + c3) | ((d0 + d1 + d2 + d3) << 16);
+              unsigned incl = tot;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+              }
+              const unsigned all = __shfl_sync(0xffffffffu, incl, 31);
+              const unsigned excl = incl - tot;
+              const unsigned s0 = carry + (excl & 0xffffu);
+              const unsigned s1 = carry + (all & 0xffffu) + (excl >> 16);
+              uint2 pc, pd;
+              pc.x = s0 | ((s0 + c0) << 16); pc.y = (s0 + c0 + c1) | ((s0 + c0 + c1 + c2) << 16);
+              pd.x = s1 | ((s1 + d0) << 16); pd.y = (s1 + d0 + d1) | ((s1 + d0 + d1 + d2) << 16);
+              *reinterpret_cast<uint2*>(WP + wbase) = pc;
+              *reinterpret_cast<uint2*>(WP + wbase + 128) = pd;
+              carry += (all & 0xffffu) + (all >> 16);
+            }
+            if (lane == 0) iflag[w] = (int)carry;
+            __syncthreads();
+            if (tid < FAST_NCH) { int o = 0; for (int i = 0; i < tid; ++i) o += iflag[i]; woffx[tid] = o; }
+            __syncthreads();
+          }
+          // ---- position: start of the fine bucket, population, own slot; shared buckets scatter ----
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k) {
+            const bool valid = lane + 32 * k < niter;
+            const unsigned fb = bo[k] & 0xffffu, off = bo[k] >> 16;
+            const unsigned word = fb >> 3, sh = (fb & 7u) * 4u;
+            const unsigned fw = FC[word];
+            const unsigned st = (unsigned)WP[word] + (unsigned)woffx[word >> 10] + nibsum(fw & ((1u << sh) - 1u));
+            const unsigned c = valid ? ((fw >> sh) & 15u) : 0u;
+            if (c >= 2u) {
+              Khi[st + off] = key_hi(x[k]);
+              if (FastKeys<T>::TWO) Klo[st + off] = key_lo(x[k]);
+            }
+            bo[k] = st | (c << 13);
+          }
+          __syncthreads();
+          // ---- resolve shared buckets (one fused loop: every round compares all 16 elements of the
+          // thread with the r-th member of their buckets; singletons and finished elements read the
+          // broadcast sentinel), finalise ranks, capture the median --------------------------------------
+          // order statistics to capture while the ranks are at hand
+          const int ncap = pass == 0 ? a.ncap : (a.p1_red.src == FS_IND ? 2 : 0);
+          const int cbase = pass == 0 ? 0 : 6;
+          const int fmA = (n & 1) ? n / 2 : n / 2 - 1, fmB = n / 2;   // median positions (pass 1)
+          unsigned vhi[FAST_EPT], acc[FAST_EPT];
+          int cmx = 0;
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k) {
+            const int c = (int)(bo[k] >> 13);
+            cmx = c > cmx ? c : cmx;
+            vhi[k] = key_hi(x[k]);
+            acc[k] = 0;
+          }
+          const int trip = __reduce_max_sync(0xffffffffu, cmx >= 2 ? cmx : 0);
+          for (int r = 0; r < trip; ++r) {
+#pragma unroll
+            for (int k = 0; k < FAST_EPT; ++k) {
+              const unsigned st = bo[k] & 0x1fffu, c = bo[k] >> 13;
+              const unsigned ce = c >= 2u ? c : 0u;
+              const unsigned yhi = Khi[(unsigned)r < ce ? st + (unsigned)r : (unsigned)FAST_SENT];
+              acc[k] += (unsigned)(yhi < vhi[k]) + ((unsigned)(yhi == vhi[k]) << 16);
+            }
+          }
+          unsigned anytie = 0;
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k) anytie |= (acc[k] >> 17);   // eqc >= 2
+          const bool slow = __any_sync(0xffffffffu, anytie != 0);
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k) {
+            const bool valid = lane + 32 * k < niter;
+            const int st = (int)(bo[k] & 0x1fffu), c = (int)(bo[k] >> 13);
+            int less = (int)(acc[k] & 0xffffu), eq = 1;
+            if (slow && (acc[k] >> 17)) {   // another member shares the hi word: exact comparison on (hi, lo)
+              const unsigned le = resolve_exact<FastKeys<T>::TWO>(Khi, Klo, st, c, vhi[k], key_lo(x[k]));
+              less = (int)(le & 0xffffu); eq = (int)(le >> 16);
+            }
+            const int lo = st + less, hi = lo + eq;
+            if (valid) {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) {
+                const int cp = pass == 0 ? a.cap_pos[c] : (c == 0 ? fmA : fmB);
+                if (c < ncap && lo <= cp && cp < hi) cap[cbase + c] = (double)x[k];
+              }
+            }
+            bo[k] = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
+          }
+          if (first_is_rankz) {
+#pragma unroll
+            for (int k = 0; k < FAST_EPT; ++k) z[k] = (lane + 32 * k < niter) ? __ldg(&a.ztab[bo[k]]) : (T)0;
+          }
+        }
+        // thresholds from the captured order statistics
+        __syncthreads();
+        if (tid == 0) {
+          if (pass == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              if (i >= a.nthr) break;
+              const FastThr th = a.thr[i];
+              const double ca = cap[th.capA], cb = cap[th.capB];
+              double v;
+              if (!th.quantile) v = (n & 1) ? ca : (double)((T)((T)ca / (T)2 + (T)cb / (T)2));
+              else if (th.f32) {
+                const float fa = (float)ca, fb = (float)cb, g = (float)th.g;
+                v = (isfinite(fa) && isfinite(fb)) ? (double)__fadd_rn(fa, __fmul_rn(g, __fsub_rn(fb, fa)))
+                                                   : (double)__fadd_rn(__fmul_rn(__fsub_rn(1.f, g), fa), __fmul_rn(g, fb));
+              } else {
+                v = (isfinite(ca) && isfinite(cb)) ? __dadd_rn(ca, __dmul_rn(th.g, __dsub_rn(cb, ca)))
+                                                   : __dadd_rn(__dmul_rn(__dsub_rn(1.0, th.g), ca), __dmul_rn(th.g, cb));
+              }
+              thrv[i] = v;
+            }
+          } else if (a.p1_red.src == FS_IND) {
+            thrv[3] = (n & 1) ? cap[6] : (double)((T)((T)cap[6] / (T)2 + (T)cap[7] / (T)2));
+          }
+        }
+        __syncthreads();
+      }
+
+      for (int r = 0; r < nred; ++r) {
+      const FastRed rd = pass == 1 ? a.p1_red : (r == 0 ? a.p0_red[0] : (r == 1 ? a.p0_red[1] : a.p0_red[2]));
+      const int slot = pass == 0 ? r : 3;
+      // ---- the series this reduction runs on -----------------------------------------------------
+      if (rd.src == FS_X) {
+#pragma unroll
+        for (int k = 0; k < FAST_EPT; ++k) z[k] = x[k];
+      } else if (rd.src == FS_IND) {
+        const double tv = thrv[pass == 0 ? rd.thr : 3];
+#pragma unroll
+        for (int k = 0; k < FAST_EPT; ++k) z[k] = ((double)x[k] <= tv) ? (T)1 : (T)0;
+      } else if (rd.src == FS_SQDEV) {
+        double sx = 0.0;
+#pragma unroll
+        for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) sx += (double)x[k];
+        sx = warp_sum(sx);
+        __syncthreads();
+        if (lane == 0) wred[w] = sx;
+        __syncthreads();
+        double tot = 0.0;
+#pragma unroll
+        for (int i = 0; i < FAST_NCH; ++i) tot += wred[i];
+        const T mean_all = (T)(tot / (double)n);
+#pragma unroll
+        for (int k = 0; k < FAST_EPT; ++k) { const T d = x[k] - mean_all; z[k] = d * d; }
+      }
+
+      // ---- split-chain moments: warp w owns split chain w -------------------------------------------
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) s += (double)z[k];
+      s = warp_sum(s);
+      const T m = (T)(s / (double)niter);
+      double q = 0.0;
+#pragma unroll
+      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) { const T d = z[k] - m; q = fma((double)d, (double)d, q); }
+      q = warp_sum(q);
+      __syncthreads();  // all resolve loops are done with K / CNT; cmean / cvar free
+      if (lane == 0) { cmean[w] = m; cvar[w] = (T)(q / (double)(niter - 1)); }
+      const bool do_ess = rd.want_ess && !a.ess_nan;
+      if (do_ess) {
+        // centred chain into the padded row: index t + (t >> 4)
+        double* row = ZC + w * FAST_ROW;
+#pragma unroll
+        for (int k = 0; k < FAST_EPT; ++k) {
+          const int t = lane + 32 * k;
+          row[t + (t >> 4)] = t < niter ? (double)(T)(z[k] - m) : 0.0;
+        }
+        for (int t = FAST_MAXITER + lane; t < FAST_TMAX; t += 32) row[t + (t >> 4)] = 0.0;
+      }
+      __syncthreads();
+      SplitGeom g8;
+      g8.niter = niter; g8.nch = FAST_NCH;
+      T W, var_plus;
+      within_between<T>(cmean, cvar, g8, W, var_plus);
+      if (tid == 0) { res[4 + slot] = (double)sqrt(var_plus / W); res[slot] = (double)Traits<T>::nan(); }
+      if (!do_ess) continue;
+
+      // ---- direct autocovariance, lazily, Geyer truncation (ess_rhat.jl:553-594) -----------------
+      const int maxlag = a.maxlag;
+      int have = 0;
+      auto batch = [&](int k0) {
+        const double* row = ZC + w * FAST_ROW;
+        double acc[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) acc[kk] = 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int t0 = 16 * lane + 8 * h;
+          double own[8], win[15];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) own[i] = row[t0 + i + lane];      // (t0+i)>>4 == lane
+#pragma unroll
+          for (int i = 0; i < 15; ++i) { const int t = t0 + k0 + i; win[i] = t < FAST_TMAX ? row[t + (t >> 4)] : 0.0; }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[kk] = fma(own[i], win[i + kk], acc[kk]);
+        }
+        const double tot = warp_reduce8(acc);
+        if ((lane & 3) == 0) part[w * 8 + (lane >> 2)] = tot;
+        __syncthreads();
+        if (tid < 8) {
+          const int k = k0 + tid;
+          if (k <= maxlag && k < niter) {
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i < FAST_NCH; ++i) sum += part[i * 8 + tid];
+            gamma[k] = (T)(sum / (double)FAST_NCH) / (T)niter;
+          }
+        }
+        __syncthreads();
+      };
+      auto ensure = [&](int k) { while (have < k) { batch(have + 1); have += 8; } };
+      const T inv_var_plus = (T)1 / var_plus;
+      auto rho = [&](int k) -> T { return (T)1 - inv_var_plus * (W - gamma[k]); };
+      ensure(1);
+      T rho_odd = rho(1), rho_even = (T)1;
+      T p_t = rho_even + rho_odd, sum_p = p_t;
+      int k = 2;
+      while (k < maxlag - 1) {
+        ensure(k + 1);
+        rho_even = rho(k);
+        rho_odd = rho(k + 1);
+        const T delta = rho_even + rho_odd;
+        if (!(delta > (T)0)) break;
+        p_t = jl_min<T>(delta, p_t);
+        sum_p += p_t;
+        k += 2;
+      }
+      if (maxlag > 1) { ensure(k); rho_even = rho(k); } else rho_even = (T)0;
+      const T tau = jl_max<T>((T)0, (T)2 * sum_p + jl_max<T>((T)0, rho_even) - (T)1);
+      T e = jl_min<T>((T)1 / tau, a.rel_ess_max);
+      if (!a.relative) e *= (T)(niter * FAST_NCH);
+      if (tid == 0) res[slot] = (double)e;
+      }   // reductions
+      if (redo) break;
+    }
+
+    if (redo) {
+      if (tid == 0) { const int idx = atomicAdd(a.redo_count, 1); a.redo_list[idx] = (int)param; }
+    } else if (tid == 0) {
+      if (a.ess_out) {
+        T e = (T)res[a.ess_mode == 4 ? 3 : 0];
+        if (a.ess_mode == 2) e = jl_min<T>(e, (T)res[1]);
+        a.ess_out[param] = e;
+      }
+      if (a.rhat_out) {
+        T rh = (T)res[4 + (a.rhat_mode == 2 ? 3 : 0)];
+        if (a.rhat_mode == 3) rh = jl_max<T>((T)res[4 + 3], rh);
+        a.rhat_out[param] = rh;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace mcd

@@ -135,3 +135,44 @@ def test_fast_many_params_statistics(mcd, o):
     relS = np.abs(S.cpu().numpy() - So) / np.abs(So)
     relR = np.abs(R.cpu().numpy() - Ro) / np.abs(Ro)
     assert (relS < RTOL64).mean() == 1.0 and (relR < RTOL64).mean() == 1.0, (relS.max(), relR.max())
+
+
+def test_fast_tail_and_estimators(mcd, o):
+    """Tail ESS (quantile indicators), estimator ESS kinds and tail R-hat on the fast kernel."""
+    ctx = mcd.get_context(0)
+    x = o.ar1(0.6, np.sqrt(1 - 0.36), 1000, 4, 24, rng=rng(59)) * 2 + 1
+    for split, shape in ((2, x), (1, x.reshape(500, 8, 24, order="F"))):
+        S, R = mcd.ess_rhat(shape, kind="tail", split_chains=split)
+        assert ctx.stat("last_path") == 3
+        So, Ro = o.ess_rhat(shape, kind="tail", split_chains=split)
+        assert close(S, So, RTOL64), (S, So)
+        assert close(R, Ro, RTOL64)
+        assert close(mcd.ess(shape, kind="tail", split_chains=split, tail_prob=0.3),
+                     o.ess(shape, kind="tail", split_chains=split, tail_prob=0.3), RTOL64)
+        assert ctx.stat("last_path") == 3
+        for km, ko in (("median", "median"), ("std", "std"), ("mad", "mad"), ("mean", "mean"),
+                       (mcd.Quantile(0.25), o.Quantile(0.25)), (mcd.Quantile(0.999), o.Quantile(0.999)),
+                       (mcd.Quantile(0.0), o.Quantile(0.0)), (mcd.Quantile(1.0), o.Quantile(1.0))):
+            for maxlag in (250, 3):
+                got = mcd.ess(shape, kind=km, split_chains=split, maxlag=maxlag)
+                assert ctx.stat("last_path") == 3, km
+                assert close(got, o.ess(shape, kind=ko, split_chains=split, maxlag=maxlag), RTOL64), (km, maxlag)
+    # odd n (median is an element), ties, Float32 quantile arithmetic
+    xo = o.ar1(0.3, np.sqrt(1 - 0.09), 333, 8, 10, rng=rng(60))
+    xo[:, :, 3] = np.round(xo[:, :, 3], 1)
+    for km, ko in (("median", "median"), ("mad", "mad"), (mcd.Quantile(0.1), o.Quantile(0.1))):
+        assert close(mcd.ess(xo, kind=km, split_chains=1), o.ess(xo, kind=ko, split_chains=1), RTOL64), km
+    S, R = mcd.ess_rhat(xo, kind="tail", split_chains=1)
+    So, Ro = o.ess_rhat(xo, kind="tail", split_chains=1)
+    assert close(S, So, RTOL64) and close(R, Ro, RTOL64)
+    x32 = x.astype(np.float32)
+    S, R = mcd.ess_rhat(x32, kind="tail")
+    So, Ro = o.ess_rhat(x32, kind="tail")
+    assert close(S, So, RTOL32) and close(R, Ro, RTOL32)
+    for km, ko in (("median", "median"), ("mad", "mad"), (mcd.Quantile(np.float32(0.3)), o.Quantile(np.float32(0.3))), (mcd.Quantile(0.3), o.Quantile(0.3))):
+        assert close(mcd.ess(x32, kind=km), o.ess(x32, kind=ko), RTOL32), km
+    # NaN data: the quantile error still surfaces (general kernel handles the declined slab)
+    xn = x.copy(); xn[3, 1, 2] = np.nan
+    with pytest.raises(mcd.ArgumentError):
+        mcd.ess(xn, kind="tail")
+    assert close(mcd.ess(xn, kind="median"), o.ess(xn, kind="median"), RTOL64)
