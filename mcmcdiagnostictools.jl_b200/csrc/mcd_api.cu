@@ -360,17 +360,10 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   };
   auto ind_red = [&](int i, int thr_index) { a.p0_red[i].src = FS_IND; a.p0_red[i].want_ess = 1; a.p0_red[i].thr = thr_index; };
   const bool plain1 = pg.nsteps == 1 && pg.combine == CB_PLAIN;
-  if (plain1 && (s0.transform == TR_NONE || s0.transform == TR_RANKNORM) && (s0.reduce == RD_ESS_RHAT || s0.reduce == RD_RHAT)) {
-    a.p0_rank = s0.transform == TR_RANKNORM; a.p0_nred = 1;
-    a.p0_red[0].src = a.p0_rank ? FS_RANKZ : FS_X; a.p0_red[0].want_ess = s0.reduce == RD_ESS_RHAT;
-    a.ess_mode = a.p0_red[0].want_ess; a.rhat_mode = 1;
-  } else if (plain1 && s0.transform == TR_FOLD_RANKNORM && s0.reduce == RD_RHAT) {
-    a.p0_rank = 1; a.ncap = 2; a.do_fold = 1; a.p1_red.src = FS_RANKZ; a.rhat_mode = 2;
-  } else if (pg.nsteps == 2 && pg.combine == CB_RANK && s0.transform == TR_RANKNORM &&
-             (s0.reduce == RD_ESS_RHAT || s0.reduce == RD_RHAT) && pg.steps[1].transform == TR_FOLD_RANKNORM &&
-             pg.steps[1].reduce == RD_RHAT) {
-    a.p0_rank = 1; a.ncap = 2; a.p0_nred = 1; a.p0_red[0].src = FS_RANKZ; a.p0_red[0].want_ess = s0.reduce == RD_ESS_RHAT;
-    a.do_fold = 1; a.p1_red.src = FS_RANKZ; a.ess_mode = a.p0_red[0].want_ess; a.rhat_mode = 3;
+  if (pg.nsteps == 1 && pg.combine == CB_MCSE_MEAN && s0.transform == TR_NONE && s0.reduce == RD_ESS_RHAT) {
+    a.p0_nred = 1; a.p0_red[0].src = FS_X; a.p0_red[0].want_ess = 1; a.ess_mode = 1; a.mcse_mode = 1;
+  } else if (pg.nsteps == 1 && pg.combine == CB_MCSE_STD && s0.transform == TR_STDPROXY && s0.reduce == RD_ESS_RHAT) {
+    a.p0_nred = 1; a.p0_red[0].src = FS_SQDEV; a.p0_red[0].want_ess = 1; a.ess_mode = 1; a.mcse_mode = 2;
   } else if ((pg.combine == CB_TAIL && pg.nsteps == 3) || (pg.combine == CB_TAIL_ESS && pg.nsteps == 2)) {
     // _ess(Val(:tail)): min of the two quantile-indicator ESS (src/ess_rhat.jl:301-311) [+ tail R-hat]
     if (s0.transform != TR_IND_QUANTILE || pg.steps[1].transform != TR_IND_QUANTILE) return MCD_OK;

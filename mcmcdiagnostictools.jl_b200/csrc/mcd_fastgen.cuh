@@ -43,6 +43,7 @@ template <typename T> struct FastGenArgs {
   FastRed p1_red;       // reduction on the folded data -> result slot 3 (FS_IND uses the median of the folded values)
   int ess_mode;         // 0 none, 1 slot 0, 2 min(slot 0, slot 1), 4 slot 3
   int rhat_mode;        // 0 none, 1 slot 0, 2 slot 3, 3 max(slot 3, slot 0)
+  int mcse_mode;        // 0 none, 1 mean: std(x)/sqrt(ess) (mcse.jl:45-51), 2 std: sqrt((m4/m2 - m2)/ess)/2 (mcse.jl:52-65)
   int maxlag, relative, ess_nan;
   T rel_ess_max;
   T* ess_out;
@@ -416,12 +417,43 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       if (redo) break;
     }
 
+    // mcse side statistics over all draws x chains (x still holds the raw values: no fold in these programs)
+    T mcse_a = (T)0, mcse_b = (T)0;
+    if (a.mcse_mode && !redo) {
+      auto block_total = [&](double v) -> double {
+        v = warp_sum(v);
+        __syncthreads();
+        if (lane == 0) wred[w] = v;
+        __syncthreads();
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < FAST_NCH; ++i) t += wred[i];
+        return t;
+      };
+      double sx = 0.0;
+#pragma unroll
+      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) sx += (double)x[k];
+      const T mean_all = (T)(block_total(sx) / (double)n);
+      double s2 = 0.0, s4 = 0.0;
+#pragma unroll
+      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) {
+        const T d = x[k] - mean_all;
+        const T pz = d * d;
+        s2 += (double)pz;
+        s4 = fma((double)pz, (double)pz, s4);
+      }
+      const double t2 = block_total(s2);
+      if (a.mcse_mode == 1) mcse_a = sqrt((T)(t2 / (double)(n - 1)));          // std(x; corrected)
+      else { mcse_a = (T)(t2 / (double)n); mcse_b = (T)(block_total(s4) / (double)n); }   // mean(proxy), mean(proxy^2)
+    }
     if (redo) {
       if (tid == 0) { const int idx = atomicAdd(a.redo_count, 1); a.redo_list[idx] = (int)param; }
     } else if (tid == 0) {
       if (a.ess_out) {
         T e = (T)res[a.ess_mode == 4 ? 3 : 0];
         if (a.ess_mode == 2) e = jl_min<T>(e, (T)res[1]);
+        if (a.mcse_mode == 1) e = mcse_a / sqrt(e);
+        else if (a.mcse_mode == 2) e = sqrt((mcse_b / mcse_a - mcse_a) / e) / (T)2;
         a.ess_out[param] = e;
       }
       if (a.rhat_out) {

@@ -176,3 +176,16 @@ def test_fast_tail_and_estimators(mcd, o):
     with pytest.raises(mcd.ArgumentError):
         mcd.ess(xn, kind="tail")
     assert close(mcd.ess(xn, kind="median"), o.ess(xn, kind="median"), RTOL64)
+
+
+def test_fast_mcse_mean_std(mcd, o):
+    ctx = mcd.get_context(0)
+    x = o.ar1(0.4, np.sqrt(1 - 0.16), 1000, 4, 16, rng=rng(61)) * 3 - 2
+    for kind in ("mean", "std"):
+        got = mcd.mcse(x, kind=kind)
+        assert ctx.stat("last_path") == 3
+        assert close(got, o.mcse(x, kind=kind), RTOL64), kind
+        got32 = mcd.mcse(x.astype(np.float32), kind=kind)
+        assert close(got32, o.mcse(x.astype(np.float32), kind=kind), RTOL32), kind
+    assert np.all(np.isnan(mcd.mcse(np.ones((1000, 4, 3)), kind="mean")))
+    assert np.all(np.isnan(mcd.mcse(np.ones((1000, 4, 3)), kind="std")))
