@@ -85,9 +85,16 @@ static int ensure_cap(mcd_ctx* ctx, void** p, size_t* cap, size_t need) {
 // ---------------------------------------------------------------------------------------
 // small kernels: tables and the generator
 // ---------------------------------------------------------------------------------------
+// z table for the doubled rank r2 (2 .. 2n): entry r2 - 2 of the interleaved table, and a second,
+// split copy starting at 2n whose first n entries are the integer ranks (the only ones untied data
+// touches: half the cache footprint) followed by the n - 1 half-integer ranks.
 template <typename T> __global__ void ztab_kernel(T* ztab, long long n) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < 2 * n - 1) ztab[i] = z_from_rank2<T>(i + 2, n);
+  if (i < 2 * n - 1) {
+    const T z = z_from_rank2<T>(i + 2, n);
+    ztab[i] = z;
+    ztab[2 * n + (i >> 1) + ((i & 1) ? n : 0)] = z;
+  }
 }
 
 template <typename T> __global__ void twiddle_kernel(Cx<T>* tw, int N) {
@@ -185,7 +192,7 @@ static long long nextprod23(long long n) {
 static int ensure_ztab(mcd_ctx* ctx, int dtype, long long n) {
   if (ctx->ztab && ctx->ztab_n == n && ctx->ztab_dtype == dtype) return MCD_OK;
   size_t ts = dtype == MCD_F64 ? 8 : 4;
-  int rc = ensure_cap(ctx, &ctx->ztab, &ctx->ztab_cap, (size_t)(2 * n - 1) * ts);
+  int rc = ensure_cap(ctx, &ctx->ztab, &ctx->ztab_cap, (size_t)(4 * n) * ts);
   if (rc) return rc;
   long long cnt = 2 * n - 1;
   int blocks = (int)((cnt + 255) / 256);
@@ -395,7 +402,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   if (lean ? (a.rank_x || a.do_tail) : (ga.p0_rank || ga.do_fold)) {
     int rc = ensure_ztab(ctx, dtype, g.n);
     if (rc) return rc;
-    a.ztab = ga.ztab = (const T*)ctx->ztab;
+    a.ztab = ga.ztab = (const T*)ctx->ztab + 2 * (size_t)g.n;   // split layout
   }
   int rc = ensure_cap(ctx, (void**)&ctx->d_redo, &ctx->redo_cap, (size_t)(params + 1) * sizeof(int));
   if (rc) return rc;

@@ -88,7 +88,7 @@ template <typename T> struct FastArgs {
   T rel_ess_max;
   T* ess_out;
   T* rhat_out;
-  const T* ztab;        // [2n-1]
+  const T* ztab;        // split layout: [n integer ranks][n-1 half ranks]
   int nbuckets;         // FAST_FINE
   int bucket_limit;     // unused (a 4-bit counter caps a bucket at 15)
   int* redo_list;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
         if (!is_const && (!(range < (T)CUDART_INF) || !(scale > (T)0) || !(scale < (T)CUDART_INF))) { redo = true; break; }
         if (is_const) {
           // every value ties: rank (n+1)/2
-          const T zc = __ldg(&a.ztab[n - 1]);
+          const T zc = __ldg(&a.ztab[((n - 1) >> 1) + (((n - 1) & 1) ? n : 0)]);
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) z[k] = zc;
           if (pass == 0 && tid == 0) { thr[0] = (double)vmin; thr[1] = (double)vmin; }
@@ -355,7 +355,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
               if (lo <= mA && mA < hi) thr[0] = (double)x[k];
               if (lo <= mB && mB < hi) thr[1] = (double)x[k];
             }
-            bo[k] = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
+            const unsigned zi = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
+            bo[k] = (zi >> 1) + ((zi & 1u) ? (unsigned)n : 0u);   // split z table: integer ranks first
           }
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) z[k] = (lane + 32 * k < niter) ? __ldg(&a.ztab[bo[k]]) : (T)0;

@@ -48,7 +48,7 @@ template <typename T> struct FastGenArgs {
   T rel_ess_max;
   T* ess_out;
   T* rhat_out;
-  const T* ztab;        // [2n-1]
+  const T* ztab;        // split layout: [n integer ranks][n-1 half ranks]
   int* redo_list;
   int* redo_count;
 };
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
         if (!is_const && (!(range < (T)CUDART_INF) || !(scale > (T)0) || !(scale < (T)CUDART_INF))) { redo = true; break; }
         if (is_const) {
           // every value ties: rank (n+1)/2
-          const T zc = __ldg(&a.ztab[n - 1]);
+          const T zc = __ldg(&a.ztab[((n - 1) >> 1) + (((n - 1) & 1) ? n : 0)]);
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) z[k] = zc;
           if (tid < 8) cap[tid] = (double)vmin;   // every order statistic equals the common value
@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
                 if (c < ncap && lo <= cp && cp < hi) cap[cbase + c] = (double)x[k];
               }
             }
-            bo[k] = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
+            const unsigned zi = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
+            bo[k] = (zi >> 1) + ((zi & 1u) ? (unsigned)n : 0u);   // split z table: integer ranks first
           }
           if (first_is_rankz) {
 #pragma unroll
