@@ -283,7 +283,15 @@ static int run_slab(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   a.flags = ctx->d_flags;
   a.redo_list = redo_list; a.redo_count = redo_count;
   if (g.nch > 4096 || pg.nsuper > 4096) return MCD_OK;
-  const size_t smem = slab_layout<T>(a, pg);
+  size_t smem = slab_layout<T>(a, pg);
+  // two CTAs per SM beat finer buckets: halve the bucket count when that is what it takes to fit two
+  const size_t two_cta = ((size_t)ctx->smem_optin + 1024 - 2 * 1024) / 2;   // (228 KB - 1 KB per CTA) / 2
+  if (smem > two_cta && a.nbuckets > 2 * SLAB_THREADS) {
+    const int full = a.nbuckets;
+    a.nbuckets = full / 2;
+    const size_t s2 = slab_layout<T>(a, pg);
+    if (s2 <= two_cta) smem = s2; else { a.nbuckets = full; smem = slab_layout<T>(a, pg); }
+  }
   if (smem > (size_t)ctx->smem_optin) return MCD_OK;  // not handled: caller uses the large path
 
   const int dtype = sizeof(T) == 8 ? MCD_F64 : MCD_F32;

@@ -348,3 +348,25 @@ def test_host_chunking_matches(mcd):
     finally:
         ctx.set_option("h2d_chunk_bytes", 256 << 20)
     assert np.array_equal(S, S2) and np.array_equal(R, R2)
+
+
+def test_empty_and_degenerate_shapes(mcd, o):
+    import warnings
+    S, R = mcd.ess_rhat(np.zeros((100, 4, 0)))
+    assert S.shape == (0,) and R.shape == (0,)
+    assert mcd.rhat(np.zeros((100, 4, 0, 3))).shape == (0, 3)
+    r = rng(70)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for shape, split in (((3, 2, 4), 2), ((2, 1, 3), 2), ((1, 4, 2), 2), ((5, 1, 2), 1), ((6, 3, 2), 3)):
+            x = r.standard_normal(shape)
+            for kind in ("rank", "basic", "tail"):
+                S, R = mcd.ess_rhat(x, kind=kind, split_chains=split)
+                So, Ro = o.ess_rhat(x, kind=kind, split_chains=split)
+                assert close(S, So, RTOL64) and close(R, Ro, RTOL64), (shape, split, kind, R, Ro)
+    # one chain: uncorrected between-chain variance (src/ess_rhat.jl:403,541)
+    x1 = o.ar1(0.3, 1.0, 400, 1, 3, rng=rng(71))
+    for split in (1, 2):
+        S, R = mcd.ess_rhat(x1, split_chains=split)
+        So, Ro = o.ess_rhat(x1, split_chains=split)
+        assert close(S, So, RTOL64) and close(R, Ro, RTOL64)
