@@ -9,9 +9,11 @@ What it is: a line-by-line NumPy/SciPy restatement of the reference algorithm
 keeps Float32 arithmetic, Float64 keeps Float64).  Every function cites the reference
 file:line it follows.
 
-PARITY STATUS: **parity unpinned by golden vectors.**  The reference is 100 % Julia and no
+PARITY STATUS: **pinned on every known-answer test and identity the reference's own test-suite
+holds for this path; no reference-output pin exists.**  The reference is 100 % Julia and no
 Julia binary exists in this image (nor on the GPU box), so the reference itself cannot be
-run here, and its test-suite holds no literal golden vectors for ESS / R-hat / MCSE.  What
+run here, and its test-suite holds no literal golden vectors for ESS / R-hat / MCSE (SURVEY
+§8(c)): parity against the reference's *outputs* is therefore unpinned.  What
 *is* pinned (tests/test_oracle_anchors.py): the `copyto_split!` index goldens
 (test/utils.jl:26-56), the antithetic cap identity `max(ess) == ntotal*log10(ntotal)`
 (test/ess_rhat.jl:314-327), constants => NaN (:242-257), monotone-transform invariance of
