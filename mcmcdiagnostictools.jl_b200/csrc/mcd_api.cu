@@ -326,17 +326,15 @@ template <typename T>
 static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom& g, const Program& pg,
                     T* d_ess, T* d_rhat, bool* handled) {
   *handled = false;
-  // 1, 2, 4, 8, 16 or 32 split chains, no discarded rows, at most 4096 values per slab
-  if ((g.nch & (g.nch - 1)) != 0 || g.nch > 32 || g.rem != 0 || g.niter < 2 || g.n > FAST_NCH * FAST_MAXITER || params >= (1ll << 31)) return MCD_OK;
+  if (g.nch != FAST_NCH || g.rem != 0 || g.niter < 2 || g.niter > FAST_MAXITER || params >= (1ll << 31)) return MCD_OK;
   if (pg.want_arr || pg.chain_inds) return MCD_OK;
   const bool ess_live = pg.want_ess && !pg.ess_nan;
   if (ess_live && pg.method != MCD_AUTOCOV_DIRECT) return MCD_OK;
   FastArgs<T> a;
   memset(&a, 0, sizeof a);
-  bool lean = g.nch == FAST_NCH;   // the lean kernel is the 8-chain specialisation
+  bool lean = true;
   const Step& s0 = pg.steps[0];
-  if (!lean) {
-  } else if (pg.nsteps == 1 && pg.combine == CB_PLAIN && (s0.transform == TR_NONE || s0.transform == TR_RANKNORM) &&
+  if (pg.nsteps == 1 && pg.combine == CB_PLAIN && (s0.transform == TR_NONE || s0.transform == TR_RANKNORM) &&
       (s0.reduce == RD_ESS_RHAT || s0.reduce == RD_RHAT)) {
     a.do_bulk = 1; a.rank_x = s0.transform == TR_RANKNORM; a.want_ess = s0.reduce == RD_ESS_RHAT;
   } else if (pg.nsteps == 1 && pg.combine == CB_PLAIN && s0.transform == TR_FOLD_RANKNORM && s0.reduce == RD_RHAT) {
@@ -377,18 +375,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   };
   auto ind_red = [&](int i, int thr_index) { a.p0_red[i].src = FS_IND; a.p0_red[i].want_ess = 1; a.p0_red[i].thr = thr_index; };
   const bool plain1 = pg.nsteps == 1 && pg.combine == CB_PLAIN;
-  if (plain1 && (s0.transform == TR_NONE || s0.transform == TR_RANKNORM) && (s0.reduce == RD_ESS_RHAT || s0.reduce == RD_RHAT)) {
-    a.p0_rank = s0.transform == TR_RANKNORM; a.p0_nred = 1;
-    a.p0_red[0].src = a.p0_rank ? FS_RANKZ : FS_X; a.p0_red[0].want_ess = s0.reduce == RD_ESS_RHAT;
-    a.ess_mode = a.p0_red[0].want_ess; a.rhat_mode = 1;
-  } else if (plain1 && s0.transform == TR_FOLD_RANKNORM && s0.reduce == RD_RHAT) {
-    a.p0_rank = 1; a.ncap = 2; a.do_fold = 1; a.p1_red.src = FS_RANKZ; a.rhat_mode = 2;
-  } else if (pg.nsteps == 2 && pg.combine == CB_RANK && s0.transform == TR_RANKNORM &&
-             (s0.reduce == RD_ESS_RHAT || s0.reduce == RD_RHAT) && pg.steps[1].transform == TR_FOLD_RANKNORM &&
-             pg.steps[1].reduce == RD_RHAT) {
-    a.p0_rank = 1; a.ncap = 2; a.p0_nred = 1; a.p0_red[0].src = FS_RANKZ; a.p0_red[0].want_ess = s0.reduce == RD_ESS_RHAT;
-    a.do_fold = 1; a.p1_red.src = FS_RANKZ; a.ess_mode = a.p0_red[0].want_ess; a.rhat_mode = 3;
-  } else if (pg.nsteps == 1 && pg.combine == CB_MCSE_MEAN && s0.transform == TR_NONE && s0.reduce == RD_ESS_RHAT) {
+  if (pg.nsteps == 1 && pg.combine == CB_MCSE_MEAN && s0.transform == TR_NONE && s0.reduce == RD_ESS_RHAT) {
     a.p0_nred = 1; a.p0_red[0].src = FS_X; a.p0_red[0].want_ess = 1; a.ess_mode = 1; a.mcse_mode = 1;
   } else if (pg.nsteps == 1 && pg.combine == CB_MCSE_STD && s0.transform == TR_STDPROXY && s0.reduce == RD_ESS_RHAT) {
     a.p0_nred = 1; a.p0_red[0].src = FS_SQDEV; a.p0_red[0].want_ess = 1; a.ess_mode = 1; a.mcse_mode = 2;
@@ -415,7 +402,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
     a.p0_rank = 1; a.ncap = 2; a.do_fold = 1; a.p1_red.src = FS_IND; a.p1_red.want_ess = 1; a.ess_mode = 4;
   } else return MCD_OK;
   }
-  a.x = ga.x = dx; a.params = ga.params = params; a.niter = ga.niter = g.niter; ga.nch = g.nch;
+  a.x = ga.x = dx; a.params = ga.params = params; a.niter = ga.niter = g.niter;
   a.maxlag = ga.maxlag = pg.maxlag; a.relative = ga.relative = pg.relative; a.ess_nan = ga.ess_nan = pg.ess_nan;
   a.rel_ess_max = ga.rel_ess_max = rel_ess_max_of<T>((long long)g.niter * g.nch);
   a.ess_out = ga.ess_out = d_ess; a.rhat_out = ga.rhat_out = d_rhat;
@@ -435,7 +422,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(a);
   } else {
-    const size_t smem = fast_smem_bytes<T>(pg.maxlag) + 1152 + (size_t)ctx->fast_pad_smem;
+    const size_t smem = fast_smem_bytes<T>(pg.maxlag) + 16 * 8 + (size_t)ctx->fast_pad_smem;
     auto kern = fastgen_kernel<T>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(ga);

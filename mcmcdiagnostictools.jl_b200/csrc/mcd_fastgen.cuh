@@ -10,11 +10,7 @@
 // The order statistics behind the thresholds (median, type-7 quantile neighbours) are captured
 // while the ranks are at hand; thresholds are then formed exactly as the reference does and the
 // indicator compares the values themselves against them.
-// It also covers every split-chain count that divides or multiplies the 8 warps of the CTA:
-// 1, 2, 4 chains (8, 4, 2 warps per chain) and 8, 16, 32 chains (1, 2, 4 chains per warp, a
-// half / quarter warp per chain in the autocovariance), with draws * chains <= 4096 and no
-// discarded rows.  The headline programs on exactly 8 split chains (rank / bulk / basic / tail
-// R-hat) stay on the leaner mcd_fast.cuh kernel.
+// The headline programs (rank / bulk / basic / tail R-hat) stay on the leaner mcd_fast.cuh kernel.
 #pragma once
 #include "mcd_fast.cuh"
 
@@ -34,8 +30,7 @@ struct FastThr { int quantile, capA, capB, f32; double g; };
 template <typename T> struct FastGenArgs {
   const T* x;
   long long params;
-  int niter;            // draws per split chain
-  int nch;              // split chains: 1, 2, 4, 8, 16 or 32; n = nch * niter <= 4096
+  int niter;            // draws per split chain; n = 8 * niter
   // pass 0 works on x, pass 1 (do_fold) on |x - median(x)|
   int p0_rank;          // pass 0 needs the ranks of x (for z, or for order statistics)
   int p0_nred;          // reductions on pass-0 data -> result slots 0..2
@@ -62,53 +57,35 @@ template <typename T>
 __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenArgs<T> a) {
   using Key = typename Traits<T>::Key;
   extern __shared__ __align__(16) unsigned char smem[];
-  const int nch = a.nch;
-  const int n = nch * a.niter;
+  const int n = FAST_NCH * a.niter;
   unsigned* FC = reinterpret_cast<unsigned*>(smem);
   unsigned short* WP = reinterpret_cast<unsigned short*>(smem + FAST_OFF_WP);
   unsigned* Khi = reinterpret_cast<unsigned*>(smem + FAST_OFF_KHI);
   unsigned* Klo = reinterpret_cast<unsigned*>(smem + FAST_OFF_KLO);
   double* ZC = reinterpret_cast<double*>(smem);
   unsigned char* small = smem + FAST_OFF_SMALL;
-  T* cmean = reinterpret_cast<T*>(small);                  // [32]
-  T* cvar = cmean + 32;                                    // [32]
-  double* part = reinterpret_cast<double*>(small + 512);   // [8][8]
+  T* cmean = reinterpret_cast<T*>(small);                  // [8]
+  T* cvar = cmean + 8;                                     // [8]
+  double* part = reinterpret_cast<double*>(small + 128);   // [8][8]
   double* wred = part + 64;                                // [2][8]
   double* cap = wred + 16;                                 // [8] captured order statistics (6,7: folded median)
   double* thrv = cap + 8;                                  // [4] thresholds (3: median of the folded values)
   double* res = thrv + 4;                                  // [8] ess[4], rhat[4] per result slot
-  double* psum = res + 8;                                  // [32] per (chain, warp-within-chain) partial sums
-  double* pq = psum + 32;                                  // [32]
-  int* iflag = reinterpret_cast<int*>(pq + 32);            // [8] warp totals / flags
+  int* iflag = reinterpret_cast<int*>(res + 8);            // [8] warp totals / flags
   int* woffx = iflag + 8;                                  // [8] exclusive warp offsets
   T* gamma = reinterpret_cast<T*>(woffx + 8);              // [maxlag + 9]
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int niter = a.niter;
   if (tid == 0) Khi[FAST_SENT] = 0xffffffffu;   // compares greater than every finite key, equal to none
-  // chain geometry: cpw chains per warp (nch >= 8) or wpc warps per chain (nch < 8)
-  const int cpw = nch >= 8 ? (nch >> 3) : 1;
-  const int wpc = nch >= 8 ? 1 : 8 / nch;
-  const int spc_shift = cpw == 1 ? 4 : (cpw == 2 ? 3 : 2);   // register slots per chain = 16 / cpw
-  const int spc_mask = (1 << spc_shift) - 1;
-  const int cbase = nch >= 8 ? w * cpw : w / wpc;            // first chain of this warp
-  const int sub = nch >= 8 ? 0 : w % wpc;                    // which 512-draw part of the chain
-  const int tbase = sub * 512;
-  // slot k of this thread: chain cbase + (k >> spc_shift), draw tbase + lane + 32 (k & spc_mask)
-  unsigned vmask = 0;
-#pragma unroll
-  for (int k = 0; k < FAST_EPT; ++k) vmask |= (unsigned)(tbase + lane + 32 * (k & spc_mask) < niter) << k;
-  // padded chain rows of the centred series: row stride rs, zero-filled on [niter, tmax)
-  const int tmax = ((niter + 15) & ~15) + 64;
-  const int rs = tmax + (tmax >> 4) + 1;
 
   for (long long param = blockIdx.x; param < a.params; param += gridDim.x) {
-    const T* __restrict__ src = a.x + param * (long long)n;
+    const T* __restrict__ src = a.x + param * (long long)n + w * niter;
     T x[FAST_EPT], z[FAST_EPT];
 #pragma unroll
     for (int k = 0; k < FAST_EPT; ++k) {
-      const int gi = (cbase + (k >> spc_shift)) * niter + tbase + lane + 32 * (k & spc_mask);
-      x[k] = ((vmask >> k) & 1u) ? __ldg(&src[gi]) : (T)0;
+      const int t = lane + 32 * k;
+      x[k] = t < niter ? __ldg(&src[t]) : (T)0;
     }
     bool redo = false;
     T vmin = (T)0, vmax = (T)0;
@@ -137,7 +114,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           int bad = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            if (((vmask >> k) & 1u)) {
+            if (lane + 32 * k < niter) {
               const T v = x[k];
               bad |= (v != v);
               lmin = v < lmin ? v : lmin;
@@ -155,7 +132,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           vmin = (T)wred[0]; vmax = (T)wred[8];
           int anybad = iflag[0];
 #pragma unroll
-          for (int i = 1; i < 8; ++i) {
+          for (int i = 1; i < FAST_NCH; ++i) {
             const T p = (T)wred[i], q = (T)wred[8 + i];
             vmin = p < vmin ? p : vmin; vmax = q > vmax ? q : vmax;
             anybad |= iflag[i];
@@ -180,7 +157,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           unsigned maxoff = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            if (((vmask >> k) & 1u)) {
+            if (lane + 32 * k < niter) {
               const unsigned fb = (unsigned)bucket_of<T>(x[k], (double)vmin, (double)scale, FAST_FINE);
               const unsigned sh = (fb & 7u) * 4u;
               const unsigned off = (atomicAdd(&FC[fb >> 3], 1u << sh) >> sh) & 15u;
@@ -220,13 +197,13 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
             }
             if (lane == 0) iflag[w] = (int)carry;
             __syncthreads();
-            if (tid < 8) { int o = 0; for (int i = 0; i < tid; ++i) o += iflag[i]; woffx[tid] = o; }
+            if (tid < FAST_NCH) { int o = 0; for (int i = 0; i < tid; ++i) o += iflag[i]; woffx[tid] = o; }
             __syncthreads();
           }
           // ---- position: start of the fine bucket, population, own slot; shared buckets scatter ----
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            const bool valid = ((vmask >> k) & 1u);
+            const bool valid = lane + 32 * k < niter;
             const unsigned fb = bo[k] & 0xffffu, off = bo[k] >> 16;
             const unsigned word = fb >> 3, sh = (fb & 7u) * 4u;
             const unsigned fw = FC[word];
@@ -271,7 +248,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           const bool slow = __any_sync(0xffffffffu, anytie != 0);
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            const bool valid = ((vmask >> k) & 1u);
+            const bool valid = lane + 32 * k < niter;
             const int st = (int)(bo[k] & 0x1fffu), c = (int)(bo[k] >> 13);
             int less = (int)(acc[k] & 0xffffu), eq = 1;
             if (slow && (acc[k] >> 17)) {   // another member shares the hi word: exact comparison on (hi, lo)
@@ -291,7 +268,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           }
           if (first_is_rankz) {
 #pragma unroll
-            for (int k = 0; k < FAST_EPT; ++k) z[k] = (((vmask >> k) & 1u)) ? __ldg(&a.ztab[bo[k]]) : (T)0;
+            for (int k = 0; k < FAST_EPT; ++k) z[k] = (lane + 32 * k < niter) ? __ldg(&a.ztab[bo[k]]) : (T)0;
           }
         }
         // thresholds from the captured order statistics
@@ -336,75 +313,45 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       } else if (rd.src == FS_SQDEV) {
         double sx = 0.0;
 #pragma unroll
-        for (int k = 0; k < FAST_EPT; ++k) if (((vmask >> k) & 1u)) sx += (double)x[k];
+        for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) sx += (double)x[k];
         sx = warp_sum(sx);
         __syncthreads();
         if (lane == 0) wred[w] = sx;
         __syncthreads();
         double tot = 0.0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) tot += wred[i];
+        for (int i = 0; i < FAST_NCH; ++i) tot += wred[i];
         const T mean_all = (T)(tot / (double)n);
 #pragma unroll
         for (int k = 0; k < FAST_EPT; ++k) { const T d = x[k] - mean_all; z[k] = d * d; }
       }
 
-      // ---- split-chain moments: a warp holds cpw chains (or one of wpc parts of a chain); partial
-      // sums meet in shared memory and are combined in a fixed order --------------------------------
+      // ---- split-chain moments: warp w owns split chain w -------------------------------------------
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) s += (double)z[k];
+      s = warp_sum(s);
+      const T m = (T)(s / (double)niter);
+      double q = 0.0;
+#pragma unroll
+      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) { const T d = z[k] - m; q = fma((double)d, (double)d, q); }
+      q = warp_sum(q);
+      __syncthreads();  // all resolve loops are done with K / CNT; cmean / cvar free
+      if (lane == 0) { cmean[w] = m; cvar[w] = (T)(q / (double)(niter - 1)); }
       const bool do_ess = rd.want_ess && !a.ess_nan;
-      __syncthreads();  // all resolve loops are done with K / CNT; the small arrays are free
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < cpw) {
-          double sacc = 0.0;
-#pragma unroll
-          for (int k = 0; k < FAST_EPT; ++k) if (((vmask >> k) & 1u) && (k >> spc_shift) == c) sacc += (double)z[k];
-          sacc = warp_sum(sacc);
-          if (lane == 0) psum[(cbase + c) * wpc + sub] = sacc;
-        }
-      }
-      __syncthreads();
-      T mloc[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        mloc[c] = (T)0;
-        if (c < cpw) {
-          double tot = 0.0;
-          for (int u = 0; u < wpc; ++u) tot += psum[(cbase + c) * wpc + u];
-          mloc[c] = (T)(tot / (double)niter);
-          double qacc = 0.0;
-#pragma unroll
-          for (int k = 0; k < FAST_EPT; ++k)
-            if (((vmask >> k) & 1u) && (k >> spc_shift) == c) { const T d = z[k] - mloc[c]; qacc = fma((double)d, (double)d, qacc); }
-          qacc = warp_sum(qacc);
-          if (lane == 0) pq[(cbase + c) * wpc + sub] = qacc;
-        }
-      }
       if (do_ess) {
-        // centred series into the padded rows: row chain * rs, index t + (t >> 4); zero tail
+        // centred chain into the padded row: index t + (t >> 4)
+        double* row = ZC + w * FAST_ROW;
 #pragma unroll
         for (int k = 0; k < FAST_EPT; ++k) {
-          if ((vmask >> k) & 1u) {
-            const int c = k >> spc_shift, t = tbase + lane + 32 * (k & spc_mask);
-            ZC[(cbase + c) * rs + t + (t >> 4)] = (double)(T)(z[k] - mloc[c]);
-          }
+          const int t = lane + 32 * k;
+          row[t + (t >> 4)] = t < niter ? (double)(T)(z[k] - m) : 0.0;
         }
-        const int tail = tmax - niter;
-        for (int i = tid; i < nch * tail; i += FAST_THREADS) {
-          const int c = i / tail, t = niter + (i - c * tail);
-          ZC[c * rs + t + (t >> 4)] = 0.0;
-        }
-      }
-      __syncthreads();
-      if (tid < nch) {
-        double tot = 0.0, qt = 0.0;
-        for (int u = 0; u < wpc; ++u) { tot += psum[tid * wpc + u]; qt += pq[tid * wpc + u]; }
-        cmean[tid] = (T)(tot / (double)niter);
-        cvar[tid] = (T)(qt / (double)(niter - 1));
+        for (int t = FAST_MAXITER + lane; t < FAST_TMAX; t += 32) row[t + (t >> 4)] = 0.0;
       }
       __syncthreads();
       SplitGeom g8;
-      g8.niter = niter; g8.nch = nch;
+      g8.niter = niter; g8.nch = FAST_NCH;
       T W, var_plus;
       within_between<T>(cmean, cvar, g8, W, var_plus);
       if (tid == 0) { res[4 + slot] = (double)sqrt(var_plus / W); res[slot] = (double)Traits<T>::nan(); }
@@ -414,22 +361,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       const int maxlag = a.maxlag;
       int have = 0;
       auto batch = [&](int k0) {
-        // lane -> (chain, 16-draw segment): 32 / cpw lanes per chain when a warp holds several chains
-        const int lpc = 32 / cpw;
-        const int bchain = cbase + lane / lpc;
-        const int t0s = (nch >= 8 ? (lane % lpc) : (sub * 32 + lane)) * 16;
-        const double* row = ZC + bchain * rs;
+        const double* row = ZC + w * FAST_ROW;
         double acc[8];
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) acc[kk] = 0.0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int t0 = t0s + 8 * h;
+          const int t0 = 16 * lane + 8 * h;
           double own[8], win[15];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) own[i] = (t0 + i < tmax) ? row[t0 + i + (t0s >> 4)] : 0.0;   // (t0+i)>>4 == t0s>>4
+          for (int i = 0; i < 8; ++i) own[i] = row[t0 + i + lane];      // (t0+i)>>4 == lane
 #pragma unroll
-          for (int i = 0; i < 15; ++i) { const int t = t0 + k0 + i; win[i] = t < tmax ? row[t + (t >> 4)] : 0.0; }
+          for (int i = 0; i < 15; ++i) { const int t = t0 + k0 + i; win[i] = t < FAST_TMAX ? row[t + (t >> 4)] : 0.0; }
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
 #pragma unroll
@@ -443,8 +386,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           if (k <= maxlag && k < niter) {
             double sum = 0.0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sum += part[i * 8 + tid];
-            gamma[k] = (T)(sum / (double)nch) / (T)niter;
+            for (int i = 0; i < FAST_NCH; ++i) sum += part[i * 8 + tid];
+            gamma[k] = (T)(sum / (double)FAST_NCH) / (T)niter;
           }
         }
         __syncthreads();
@@ -469,7 +412,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       if (maxlag > 1) { ensure(k); rho_even = rho(k); } else rho_even = (T)0;
       const T tau = jl_max<T>((T)0, (T)2 * sum_p + jl_max<T>((T)0, rho_even) - (T)1);
       T e = jl_min<T>((T)1 / tau, a.rel_ess_max);
-      if (!a.relative) e *= (T)(niter * nch);
+      if (!a.relative) e *= (T)(niter * FAST_NCH);
       if (tid == 0) res[slot] = (double)e;
       }   // reductions
       if (redo) break;
@@ -485,16 +428,16 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
         __syncthreads();
         double t = 0.0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += wred[i];
+        for (int i = 0; i < FAST_NCH; ++i) t += wred[i];
         return t;
       };
       double sx = 0.0;
 #pragma unroll
-      for (int k = 0; k < FAST_EPT; ++k) if (((vmask >> k) & 1u)) sx += (double)x[k];
+      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) sx += (double)x[k];
       const T mean_all = (T)(block_total(sx) / (double)n);
       double s2 = 0.0, s4 = 0.0;
 #pragma unroll
-      for (int k = 0; k < FAST_EPT; ++k) if (((vmask >> k) & 1u)) {
+      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) {
         const T d = x[k] - mean_all;
         const T pz = d * d;
         s2 += (double)pz;

@@ -194,23 +194,19 @@ def test_fast_mcse_mean_std(mcd, o):
 @pytest.mark.parametrize("shape,split", [((1000, 1), 1), ((4000, 1), 1), ((1000, 1), 2), ((2000, 2), 1), ((1000, 2), 2),
                                           ((1000, 4), 1), ((500, 8), 2), ((256, 16), 1), ((250, 8), 2), ((128, 16), 2),
                                           ((64, 32), 1), ((20, 16), 2), ((1024, 4), 1), ((333, 2), 1)])
-def test_fast_other_chain_counts(mcd, o, shape, split):
-    """1, 2, 4, 16, 32 split chains (and 8 off the lean patterns) on the general fast kernel."""
-    ctx = mcd.get_context(0)
+def test_other_chain_counts(mcd, o, shape, split):
+    """Other split-chain counts (1, 2, 4, 16, 32; whichever kernel the dispatcher picks)."""
     x = o.ar1(0.6, np.sqrt(1 - 0.36), shape[0], shape[1], 9, rng=rng(62)) + 0.3
     x[:, :, 4] = np.round(x[:, :, 4], 1)
-    nch = shape[1] * split
     for kind in ("rank", "bulk", "tail", "basic"):
         for maxlag in (250, 5):
             S, R = mcd.ess_rhat(x, kind=kind, split_chains=split, maxlag=maxlag)
-            assert ctx.stat("last_path") == 3, (shape, split, kind)
             So, Ro = o.ess_rhat(x, kind=kind, split_chains=split, maxlag=maxlag)
             assert close(S, So, RTOL64), (shape, split, kind, maxlag, S, So)
             assert close(R, Ro, RTOL64), (shape, split, kind, R, Ro)
         assert close(mcd.rhat(x, kind=kind, split_chains=split), o.rhat(x, kind=kind, split_chains=split), RTOL64)
     for km, ko in (("median", "median"), ("std", "std"), ("mad", "mad"), (mcd.Quantile(0.8), o.Quantile(0.8))):
         assert close(mcd.ess(x, kind=km, split_chains=split), o.ess(x, kind=ko, split_chains=split), RTOL64), (shape, km)
-        assert ctx.stat("last_path") == 3
     assert close(mcd.mcse(x, kind="mean", split_chains=split), o.mcse(x, kind="mean", split_chains=split), RTOL64)
     x32 = x.astype(np.float32)
     S, R = mcd.ess_rhat(x32, split_chains=split)
