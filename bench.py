@@ -229,7 +229,24 @@ def gpu_arm(args):
     e2e = None
     if not args.no_e2e:
         e2e_params = min(shard, args.e2e_params // world if args.e2e_params else shard)
-        xh_t = torch.empty((e2e_params, CHAINS, DRAWS), dtype=torch.float64, pin_memory=True)
+        # pinned staging of the whole shard (32 GB at N = 1); if the host cannot pin that much, every
+        # rank halves its sample together (the choice is agreed with an all-reduce) and the line says so
+        xh_t = None
+        while True:
+            try:
+                xh_t = torch.empty((e2e_params, CHAINS, DRAWS), dtype=torch.float64, pin_memory=True)
+                ok = 1
+            except (RuntimeError, MemoryError):
+                xh_t, ok = None, 0
+            okt = torch.tensor([ok], dtype=torch.int32, device=dev)
+            if world > 1:
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            if int(okt[0]) == 1:
+                break
+            xh_t = None
+            e2e_params //= 2
+            if e2e_params < 1000:
+                raise SystemExit("cannot pin host memory for the e2e measurement")
         xh_t.copy_(x.permute(2, 1, 0)[:e2e_params])
         torch.cuda.synchronize()
         xh = xh_t.numpy().transpose(2, 1, 0)          # (draws, chains, params) column-major view
@@ -246,7 +263,8 @@ def gpu_arm(args):
         e2e = {"value": e2e_params * world / float(tt[0]), "unit": "params/s",
                "h2d_bytes_per_step": e2e_params * world * DRAWS * CHAINS * 8,
                "d2h_bytes_per_step": e2e_params * world * 16,
-               "params_per_step": e2e_params * world, "host_memory": "pinned", "ms_per_step": float(tt[0]) * 1e3}
+               "params_per_step": e2e_params * world, "host_memory": "pinned", "ms_per_step": float(tt[0]) * 1e3,
+               "sample": "whole array" if e2e_params == shard else f"first {e2e_params} parameters of each shard (host could not pin more)"}
         # parity spot check against the device-resident result
         assert np.array_equal(Sh, S[:e2e_params].cpu().numpy()), "host-staged and device-resident results differ"
         del xh_t
