@@ -48,6 +48,7 @@ struct mcd_ctx {
   long long workspace_bytes = 6ll << 30;
   int bucket_limit = 64;
   int fast_pad_smem = 0;   // developer knob: extra dynamic shared memory (lowers CTAs/SM)
+  int fast_grid_mult = 0;  // developer knob: 0 = one CTA per parameter, k = persistent grid of k * 2 * SMs CTAs
   // stats
   long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   int last_path = 0;
@@ -420,7 +421,8 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
     const size_t smem = fast_smem_bytes<T>(pg.maxlag) + (size_t)ctx->fast_pad_smem;
     auto kern = fast_kernel<T>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(a);
+    const unsigned grid = ctx->fast_grid_mult ? (unsigned)std::min<long long>(params, (long long)ctx->fast_grid_mult * 2 * ctx->sm_count) : (unsigned)params;
+    kern<<<grid, FAST_THREADS, smem, ctx->stream>>>(a);
   } else {
     const size_t smem = fast_smem_bytes<T>(pg.maxlag) + 16 * 8 + (size_t)ctx->fast_pad_smem;
     auto kern = fastgen_kernel<T>;
@@ -678,6 +680,7 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   else if (k == "h2d_chunk_bytes") { if (value < 1) return fail(ctx, MCD_EINVAL, "h2d_chunk_bytes >= 1"); ctx->h2d_chunk_bytes = value; }
   else if (k == "workspace_bytes") { if (value < (1 << 20)) return fail(ctx, MCD_EINVAL, "workspace_bytes >= 1 MiB"); ctx->workspace_bytes = value; }
   else if (k == "fast_pad_smem") { ctx->fast_pad_smem = (int)value; }
+  else if (k == "fast_grid_mult") { ctx->fast_grid_mult = (int)value; }
   else if (k == "sort_bucket_limit") { if (value < 0) return fail(ctx, MCD_EINVAL, "sort_bucket_limit >= 0"); ctx->bucket_limit = (int)value; }
   else return fail(ctx, MCD_EINVAL, "unknown option '%s'", key);
   return MCD_OK;

@@ -167,27 +167,57 @@ __device__ inline double betainc_reg(double a, double b, double x) {
 }
 
 // inverse of I_x(a,b) = p  (StatsFuns.betainvcdf, call site src/mcse.jl:108-109).
-// Safeguarded Newton from the normal approximation; bracket kept for bisection.
+// Safeguarded Newton from the normal approximation.  The continued fraction (the expensive
+// part: O(sqrt(max(a,b))) terms) is evaluated ONCE, at the starting point; every later value of
+// I is carried forward by integrating the density over the (small) Newton step with a 5-point
+// Gauss-Legendre rule, I(x + h) = I(x) + int_x^{x+h} pdf.  A final continued-fraction check
+// polishes the root if the carried value drifted.
+__device__ inline double beta_logpdf(double a, double b, double lb, double x) {
+  return (a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lb;
+}
+__device__ inline double beta_pdf_integral(double a, double b, double lb, double x0, double x1) {
+  // 5-point Gauss-Legendre on [x0, x1]
+  const double xm = 0.5 * (x0 + x1), xr = 0.5 * (x1 - x0);
+  const double n1 = 0.5384693101056831, n2 = 0.9061798459386640;
+  const double w0 = 0.5688888888888889, w1 = 0.4786286704993665, w2 = 0.2369268850561891;
+  double s = w0 * exp(beta_logpdf(a, b, lb, xm));
+  s += w1 * (exp(beta_logpdf(a, b, lb, xm - n1 * xr)) + exp(beta_logpdf(a, b, lb, xm + n1 * xr)));
+  s += w2 * (exp(beta_logpdf(a, b, lb, xm - n2 * xr)) + exp(beta_logpdf(a, b, lb, xm + n2 * xr)));
+  return s * xr;
+}
 __device__ inline double betainc_inv(double a, double b, double p) {
   if (!(a > 0.0) || !(b > 0.0) || !(p == p)) return CUDART_NAN;
   if (p <= 0.0) return 0.0;
   if (p >= 1.0) return 1.0;
-  double mu = a / (a + b);
-  double sd = sqrt(a * b / ((a + b) * (a + b) * (a + b + 1.0)));
+  const double mu = a / (a + b);
+  const double sd = sqrt(a * b / ((a + b) * (a + b) * (a + b + 1.0)));
   double x = mu + normcdfinv(p) * sd;
   double lo = 0.0, hi = 1.0;
   if (!(x > 0.0 && x < 1.0)) x = mu;
   const double lb = lbeta(a, b);
-  for (int it = 0; it < 200; ++it) {
-    double f = betainc_reg(a, b, x) - p;
+  const bool smooth = a > 2.0 && b > 2.0;   // density bounded and smooth: the quadrature carry is safe
+  double Ix = betainc_reg(a, b, x);
+  for (int it = 0; it < 60; ++it) {
+    const double f = Ix - p;
     if (f > 0.0) hi = x; else lo = x;
     if (f == 0.0) break;
-    double lpdf = (a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lb;
-    double dx = f / exp(lpdf);
+    const double dx = f / exp(beta_logpdf(a, b, lb, x));
     double xn = x - dx;
-    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-    if (fabs(xn - x) <= 4e-16 * fabs(xn) || hi - lo <= 1e-17) { x = xn; break; }
+    bool bis = false;
+    if (!(xn > lo && xn < hi)) { xn = 0.5 * (lo + hi); bis = true; }
+    // with the carried value the iteration is only asked for ~1e-9: the exact polish below finishes it
+    const bool done = fabs(xn - x) <= (smooth ? 1e-9 : 4e-16) * fabs(xn) || hi - lo <= 1e-17;
+    if (smooth && !bis && fabs(xn - x) < 0.5 * sd) Ix += beta_pdf_integral(a, b, lb, x, xn);
+    else Ix = betainc_reg(a, b, xn);
     x = xn;
+    if (done) break;
+  }
+  if (smooth) {
+    // one exact evaluation to remove any drift of the carried value
+    // (Newton from 1e-9 is quadratically convergent: one exact step reaches ~1e-15)
+    const double f = betainc_reg(a, b, x) - p;
+    const double xn = x - f / exp(beta_logpdf(a, b, lb, x));
+    if (xn > 0.0 && xn < 1.0) x = xn;
   }
   return x;
 }

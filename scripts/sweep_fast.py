@@ -13,8 +13,8 @@ def t(fn, reps=3):
     return best
 for phi in (0.5,):
     x = m.generate_ar1(phi, np.sqrt(1 - phi * phi), 1000, 4, P, seed=1)
-    for ver, B in ((0, 65536), (1, 0)):
-        ctx.set_option('force_path', ver)
+    for ver, B in ((0, 0), (1, 0), (2, 0), (8, 0)):
+        ctx.set_option('fast_grid_mult', ver)
         for name, fn in (("rank", lambda: m.ess_rhat(x)), ("rhat rank", lambda: m.rhat(x)), ("bulk", lambda: m.ess_rhat(x, kind="bulk")), ("basic", lambda: m.ess_rhat(x, kind="basic"))):
             ms = t(fn)
-            print(f"force_path{ver} phi={phi} B={B:6d} {name:10s} {ms:8.3f} ms  {P/ms*1e3:10.4e} params/s  frac={P*32016/ms/1e6/6548.2:.4f}")
+            print(f"gridmult{ver} phi={phi} B={B:6d} {name:10s} {ms:8.3f} ms  {P/ms*1e3:10.4e} params/s  frac={P*32016/ms/1e6/6548.2:.4f}")
