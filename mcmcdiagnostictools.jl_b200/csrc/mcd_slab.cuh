@@ -423,13 +423,28 @@ __device__ __forceinline__ void within_between(const T* cmean, const T* cvar, co
 // (ess_rhat.jl:197-213) estimator on the centred samples.  Block-wide.
 template <typename T, int THREADS, bool BDA>
 __device__ void lag_batch(const T* Y, const SplitGeom& g, int k0, int kmax, double* part, T* gamma,
-                          T mean_chain_var) {
+                          T mean_chain_var, bool blocked16 = false) {
   constexpr int NW = THREADS / WARP;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double acc[LAG_BATCH];
 #pragma unroll
   for (int kk = 0; kk < LAG_BATCH; ++kk) acc[kk] = 0.0;
   const int niter = g.niter;
+  if (blocked16 && !BDA) {
+    // Same summation order as mcd_fast.cuh (lane l owns the draws [16 l, 16 l + 16), ascending), so
+    // that a slab the fast kernel hands back is computed to the same bits the fast kernel would give.
+    for (int j = w; j < g.nch; j += NW) {
+      const T* p = Y + g.chain_start(j);
+      for (int t = 16 * lane; t < 16 * lane + 16 && t + k0 < niter; ++t) {
+        const T a = p[t];
+#pragma unroll
+        for (int kk = 0; kk < LAG_BATCH; ++kk) {
+          const int tk = t + k0 + kk;
+          if (tk < niter) acc[kk] = fma((double)a, (double)p[tk], acc[kk]);
+        }
+      }
+    }
+  } else
   for (int j = w; j < g.nch; j += NW) {
     const T* p = Y + g.chain_start(j);
     for (int t = lane; t + k0 < niter; t += WARP) {
@@ -596,7 +611,7 @@ __device__ Result reduce_ess_rhat(T* Y, const SlabArgs<T>& a, unsigned char* sme
   auto ensure = [&](int k) {
     while (have < k) {
       if (a.method == 2) lag_batch<T, THREADS, true>(Y, g, have + 1, maxlag, part, gamma, W);
-      else lag_batch<T, THREADS, false>(Y, g, have + 1, maxlag, part, gamma, W);
+      else lag_batch<T, THREADS, false>(Y, g, have + 1, maxlag, part, gamma, W, a.redo_list != nullptr && g.niter <= 512);
       have += LAG_BATCH;
     }
   };
