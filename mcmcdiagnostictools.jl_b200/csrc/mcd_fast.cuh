@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int niter = a.niter;
-  if (tid == 0) Khi[FAST_SENT] = 0xffffffffu;   // compares greater than every finite key, equal to none
+  if (tid == 0) { Khi[FAST_SENT] = 0xffffffffu; Khi[FAST_SENT + 1] = 0; }   // sentinel (unused by the list resolve); list length
 
   for (long long param = blockIdx.x; param < a.params; param += gridDim.x) {
     const T* __restrict__ src = a.x + param * (long long)n + w * niter;
@@ -311,45 +311,64 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
               Khi[st + off] = key_hi(x[k]);
               if (FastKeys<T>::TWO) Klo[st + off] = key_lo(x[k]);
             }
-            bo[k] = st | (c << 13);
+            bo[k] = st | (c << 13) | (off << 17);
           }
           __syncthreads();
-          // ---- resolve shared buckets (one fused loop: every round compares all 16 elements of the
-          // thread with the r-th member of their buckets; singletons and finished elements read the
-          // broadcast sentinel), finalise ranks, capture the median --------------------------------------
+          // ---- resolve shared buckets: their members (~10 % of the values) are compacted into a work
+          // list (aliasing the dead counter words) and compared with their bucket mates by all threads;
+          // the exact (less, equal) pair of each comes back through RES (aliasing the dead prefixes) -----
           const int mA = (n & 1) ? n / 2 : n / 2 - 1, mB = n / 2;
-          unsigned vhi[FAST_EPT], acc[FAST_EPT];
-          int cmx = 0;
+          unsigned* WL = FC;
+          unsigned short* RES = WP;
+          {
+            unsigned mine = 0;
 #pragma unroll
-          for (int k = 0; k < FAST_EPT; ++k) {
-            const int c = (int)(bo[k] >> 13);
-            cmx = c > cmx ? c : cmx;
-            vhi[k] = key_hi(x[k]);
-            acc[k] = 0;
-          }
-          const int trip = __reduce_max_sync(0xffffffffu, cmx >= 2 ? cmx : 0);
-          for (int r = 0; r < trip; ++r) {
+            for (int k = 0; k < FAST_EPT; ++k) mine += ((bo[k] >> 13) & 15u) >= 2u;
+            unsigned incl = mine;
 #pragma unroll
-            for (int k = 0; k < FAST_EPT; ++k) {
-              const unsigned st = bo[k] & 0x1fffu, c = bo[k] >> 13;
-              const unsigned ce = c >= 2u ? c : 0u;
-              const unsigned yhi = Khi[(unsigned)r < ce ? st + (unsigned)r : (unsigned)FAST_SENT];
-              acc[k] += (unsigned)(yhi < vhi[k]) + ((unsigned)(yhi == vhi[k]) << 16);
+            for (int o = 1; o < 32; o <<= 1) {
+              const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            unsigned base = 0;
+            if (lane == 31) base = atomicAdd(&Khi[FAST_SENT + 1], incl);
+            unsigned q = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+            if (mine) {
+#pragma unroll
+              for (int k = 0; k < FAST_EPT; ++k) {
+                const unsigned c = (bo[k] >> 13) & 15u;
+                if (c >= 2u) WL[q++] = (unsigned)(k * FAST_THREADS + tid) | ((bo[k] & 0xfffu) << 12) | (c << 24) | ((bo[k] >> 17) << 28);
+              }
             }
           }
-          unsigned anytie = 0;
-#pragma unroll
-          for (int k = 0; k < FAST_EPT; ++k) anytie |= (acc[k] >> 17);   // eqc >= 2
-          const bool slow = __any_sync(0xffffffffu, anytie != 0);
+          __syncthreads();
+          {
+            const unsigned listn = Khi[FAST_SENT + 1];
+            for (unsigned q = tid; q < listn; q += FAST_THREADS) {
+              const unsigned it = WL[q];
+              const unsigned st = (it >> 12) & 0xfffu, c = (it >> 24) & 15u, off = it >> 28;
+              const unsigned vhi = Khi[st + off];
+              const unsigned vlo = FastKeys<T>::TWO ? Klo[st + off] : 0u;
+              unsigned less = 0, eq = 0;
+              for (unsigned j = st; j < st + c; ++j) {
+                const unsigned yhi = Khi[j];
+                if (yhi < vhi) ++less;
+                else if (yhi == vhi) {
+                  if constexpr (FastKeys<T>::TWO) { const unsigned ylo = Klo[j]; less += ylo < vlo; eq += ylo == vlo; }
+                  else ++eq;
+                }
+              }
+              RES[it & 0xfffu] = (unsigned short)(less | (eq << 8));
+            }
+          }
+          __syncthreads();
+          if (tid == 0) Khi[FAST_SENT + 1] = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
             const bool valid = lane + 32 * k < niter;
-            const int st = (int)(bo[k] & 0x1fffu), c = (int)(bo[k] >> 13);
-            int less = (int)(acc[k] & 0xffffu), eq = 1;
-            if (slow && (acc[k] >> 17)) {   // another member shares the hi word: exact comparison on (hi, lo)
-              const unsigned le = resolve_exact<FastKeys<T>::TWO>(Khi, Klo, st, c, vhi[k], key_lo(x[k]));
-              less = (int)(le & 0xffffu); eq = (int)(le >> 16);
-            }
+            const int st = (int)(bo[k] & 0x1fffu), c = (int)((bo[k] >> 13) & 15u);
+            int less = 0, eq = 1;
+            if (c >= 2) { const unsigned le = RES[k * FAST_THREADS + tid]; less = (int)(le & 0xffu); eq = (int)(le >> 8); }
             const int lo = st + less, hi = lo + eq;
             if (pass == 0 && a.do_tail && valid) {
               if (lo <= mA && mA < hi) thr[0] = (double)x[k];
