@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
           for (int i = tid; i < FAST_WORDS / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(FC)[i] = make_uint4(0, 0, 0, 0);
           __syncthreads();
           unsigned bo[FAST_EPT];   // fine bucket | arrival offset << 16 ; later: packed rank info
-          unsigned maxoff = 0;
+          unsigned maxoff = 0, shared_mask = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
             if (lane + 32 * k < niter) {
@@ -311,19 +311,20 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
               Khi[st + off] = key_hi(x[k]);
               if (FastKeys<T>::TWO) Klo[st + off] = key_lo(x[k]);
             }
-            bo[k] = st | (c << 13) | (off << 17);
+            bo[k] = st | (c << 12) | (off << 16);   // st <= 4095
+            shared_mask |= (c >= 2u ? 1u : 0u) << k;
           }
           __syncthreads();
           // ---- resolve shared buckets: their members (~10 % of the values) are compacted into a work
           // list (aliasing the dead counter words) and compared with their bucket mates by all threads;
-          // the exact (less, equal) pair of each comes back through RES (aliasing the dead prefixes) -----
+          // the z-table index of each comes back through RES (aliasing the dead prefixes).  A value
+          // alone in its bucket has the integer rank st + 1, i.e. table index st. -----------------------
           const int mA = (n & 1) ? n / 2 : n / 2 - 1, mB = n / 2;
+          const bool capture = pass == 0 && a.do_tail;
           unsigned* WL = FC;
           unsigned short* RES = WP;
           {
-            unsigned mine = 0;
-#pragma unroll
-            for (int k = 0; k < FAST_EPT; ++k) mine += ((bo[k] >> 13) & 15u) >= 2u;
+            const unsigned mine = __popc(shared_mask);
             unsigned incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -333,12 +334,11 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
             unsigned base = 0;
             if (lane == 31) base = atomicAdd(&Khi[FAST_SENT + 1], incl);
             unsigned q = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+            const unsigned slot0 = (unsigned)tid << 20;
             if (mine) {
 #pragma unroll
-              for (int k = 0; k < FAST_EPT; ++k) {
-                const unsigned c = (bo[k] >> 13) & 15u;
-                if (c >= 2u) WL[q++] = (unsigned)(k * FAST_THREADS + tid) | ((bo[k] & 0xfffu) << 12) | (c << 24) | ((bo[k] >> 17) << 28);
-              }
+              for (int k = 0; k < FAST_EPT; ++k)
+                if (shared_mask & (1u << k)) WL[q++] = bo[k] | (slot0 + ((unsigned)k << 28));   // slot = k * 256 + tid
             }
           }
           __syncthreads();
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
             const unsigned listn = Khi[FAST_SENT + 1];
             for (unsigned q = tid; q < listn; q += FAST_THREADS) {
               const unsigned it = WL[q];
-              const unsigned st = (it >> 12) & 0xfffu, c = (it >> 24) & 15u, off = it >> 28;
+              const unsigned st = it & 0xfffu, c = (it >> 12) & 15u, off = (it >> 16) & 15u;
               const unsigned vhi = Khi[st + off];
               const unsigned vlo = FastKeys<T>::TWO ? Klo[st + off] : 0u;
               unsigned less = 0, eq = 0;
@@ -358,25 +358,33 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
                   else ++eq;
                 }
               }
-              RES[it & 0xfffu] = (unsigned short)(less | (eq << 8));
+              const int lo = (int)(st + less), hi = lo + (int)eq;
+              if (capture && ((lo <= mA && mA < hi) || (lo <= mB && mB < hi))) {
+                double v;
+                if constexpr (FastKeys<T>::TWO) v = key_value(((unsigned long long)vhi << 32) | vlo);
+                else v = (double)key_value(vhi);
+                if (lo <= mA && mA < hi) thr[0] = v;
+                if (lo <= mB && mB < hi) thr[1] = v;
+              }
+              const unsigned zi = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
+              RES[it >> 20] = (unsigned short)((zi >> 1) + ((zi & 1u) ? (unsigned)n : 0u));   // split z table
             }
           }
           __syncthreads();
           if (tid == 0) Khi[FAST_SENT + 1] = 0;
+          if (capture) {
 #pragma unroll
-          for (int k = 0; k < FAST_EPT; ++k) {
-            const bool valid = lane + 32 * k < niter;
-            const int st = (int)(bo[k] & 0x1fffu), c = (int)((bo[k] >> 13) & 15u);
-            int less = 0, eq = 1;
-            if (c >= 2) { const unsigned le = RES[k * FAST_THREADS + tid]; less = (int)(le & 0xffu); eq = (int)(le >> 8); }
-            const int lo = st + less, hi = lo + eq;
-            if (pass == 0 && a.do_tail && valid) {
-              if (lo <= mA && mA < hi) thr[0] = (double)x[k];
-              if (lo <= mB && mB < hi) thr[1] = (double)x[k];
+            for (int k = 0; k < FAST_EPT; ++k) {
+              const int st = (int)(bo[k] & 0xfffu);
+              if (lane + 32 * k < niter && !(shared_mask & (1u << k))) {
+                if (st == mA) thr[0] = (double)x[k];
+                if (st == mB) thr[1] = (double)x[k];
+              }
             }
-            const unsigned zi = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
-            bo[k] = (zi >> 1) + ((zi & 1u) ? (unsigned)n : 0u);   // split z table: integer ranks first
           }
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k)
+            bo[k] = (shared_mask & (1u << k)) ? (unsigned)RES[k * FAST_THREADS + tid] : (bo[k] & 0xfffu);
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) z[k] = (lane + 32 * k < niter) ? __ldg(&a.ztab[bo[k]]) : (T)0;
         }
