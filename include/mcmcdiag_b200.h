@@ -138,6 +138,29 @@ int mcd_mcse(mcd_ctx* ctx, const void* x, int mem, int dtype,
              int autocov_method, int split_chains, int maxlag,
              void* mcse_out);
 
+/* Fused per-parameter summary: the per-parameter columns that the callers of
+ * this package (MCMCChains.summarystats, PosteriorStats.summarize) assemble from separate calls,
+ * computed in ONE call with the input crossing PCIe once.  `fields` is a mask of MCD_SUM_*; `out`
+ * receives one column of `params` values per selected field, in the order of the bit positions
+ * (column-major, params x popcount(fields), element type = dtype).  Column definitions, each
+ * identical to the reference call it replaces:
+ *   MCD_SUM_MEAN       Statistics.mean(x; dims=(1,2))          (as used at src/mcse.jl:50)
+ *   MCD_SUM_STD        Statistics.std(x; dims=(1,2))           (src/mcse.jl:50)
+ *   MCD_SUM_MCSE_MEAN  mcse(x; kind=mean, ...)                 (src/mcse.jl:45-52)
+ *   MCD_SUM_MCSE_STD   mcse(x; kind=std, ...)                  (src/mcse.jl:53-69)
+ *   MCD_SUM_ESS_BULK   ess(x; kind=:bulk, ...)                 (src/ess_rhat.jl:604-624)
+ *   MCD_SUM_ESS_TAIL   ess(x; kind=:tail, tail_prob, ...)      (src/ess_rhat.jl:298-311)
+ *   MCD_SUM_RHAT       rhat(x; kind=:rank, split_chains)       (src/ess_rhat.jl:410-420)
+ * autocov_method / split_chains / maxlag / tail_prob apply to every ESS-based column. */
+enum {
+  MCD_SUM_MEAN = 1, MCD_SUM_STD = 2, MCD_SUM_MCSE_MEAN = 4, MCD_SUM_MCSE_STD = 8,
+  MCD_SUM_ESS_BULK = 16, MCD_SUM_ESS_TAIL = 32, MCD_SUM_RHAT = 64, MCD_SUM_ALL = 127
+};
+int mcd_summary(mcd_ctx* ctx, const void* x, int mem, int dtype,
+                int64_t draws, int64_t chains, int64_t params,
+                unsigned fields, int autocov_method, int split_chains, int maxlag,
+                double tail_prob, int tail_prob_f64, void* out);
+
 /* rhat_nested: `_rhat_nested(::Val{kind}, x, chain_inds; split_chains)` +
  * `_rhat_nested_basic!` (src/rhat_nested.jl:83-188).  chain_inds is a HOST array,
  * column-major (chains_per_super x nsuper), 0-based chain indices, as produced by

@@ -34,10 +34,12 @@ __all__ = [
     "ESSMethod", "FFTESSMethod", "BDAESSMethod",
     "Quantile", "ArgumentError", "DomainError", "DimensionMismatch",
     "Context", "get_context", "tiedrank", "rank_normalize", "fold_around_median",
-    "generate_ar1", "ESSRhat",
+    "generate_ar1", "ESSRhat", "summary", "SUMMARY_FIELDS",
 ]
 
 ESSRhat = namedtuple("ESSRhat", ["ess", "rhat"])
+# columns of `summary`, in the bit order of MCD_SUM_* (include/mcmcdiag_b200.h)
+SUMMARY_FIELDS = ("mean", "std", "mcse_mean", "mcse_std", "ess_bulk", "ess_tail", "rhat")
 
 
 class ArgumentError(ValueError):
@@ -427,6 +429,46 @@ def mcse(samples, *, kind=np.mean, ctx=None, **kwargs):
     a = _Arr(samples)
     kwargs.pop("relative", None)
     return _call_estimator(a, est, ctx=ctx, mcse_mode=True, **kwargs)
+
+
+def summary(samples, *, fields=None, autocov_method=None, split_chains=2, maxlag=250,
+            tail_prob=Fraction(1, 10), ctx=None):
+    """Fused per-parameter summary: a dict of the columns `SUMMARY_FIELDS`,
+
+        mean      = Statistics.mean(x; dims=(1,2))        std       = Statistics.std(x; dims=(1,2))
+        mcse_mean = mcse(x; kind=mean, kw...)             mcse_std  = mcse(x; kind=std, kw...)
+        ess_bulk  = ess(x; kind=:bulk, kw...)             ess_tail  = ess(x; kind=:tail, tail_prob, kw...)
+        rhat      = rhat(x; kind=:rank, split_chains)
+
+    each identical to the separate reference call (src/mcse.jl:45-69, src/ess_rhat.jl:298-311,
+    410-420, 604-624), computed by one library call that stages a host array once."""
+    names = SUMMARY_FIELDS if fields is None else tuple(fields)
+    for f in names:
+        if f not in SUMMARY_FIELDS:
+            raise ArgumentError(f"unknown summary field `{f}`; expected a subset of {SUMMARY_FIELDS}")
+    if not names:
+        raise ArgumentError("no summary field requested")
+    names = tuple(f for f in SUMMARY_FIELDS if f in names)   # library column order
+    mask = sum(1 << SUMMARY_FIELDS.index(f) for f in names)
+    _check_split(split_chains)
+    a = _Arr(samples)
+    ctx = a.context(ctx)
+    method = _method_code(autocov_method if autocov_method is not None else AutocovMethod())
+    if mask & 0b0111100:
+        _warn_niter(a, split_chains)
+        if a.draws // split_chains > 4 and not maxlag > 0:
+            raise DomainError(f"maxlag must be >0. (got {maxlag})")
+    tp, tp64 = _tail_prob(tail_prob)
+    if a.is_torch:
+        import torch
+        out = torch.empty((len(names), a.nparams), dtype=a.torch_dtype, device=a.torch_device)
+    else:
+        out = np.empty((len(names), a.nparams), dtype=a.dtype)
+    rc = ctx._lib.mcd_summary(ctx._h, C.c_void_p(a.ptr), a.mem, a.code, a.draws, a.chains, a.nparams,
+                              mask, method, int(split_chains), int(max(min(maxlag, 2**31 - 1), -1)),
+                              tp, tp64, a.out_ptr(out))
+    ctx.check(rc, domain=True)
+    return {f: a.finish(out[i]) for i, f in enumerate(names)}
 
 
 def _validate_superchain_ids(superchain_ids, nchains):

@@ -39,7 +39,7 @@ struct mcd_ctx {
   int* d_redo = nullptr; size_t redo_cap = 0;   // [0] = count, [1..] = parameter indices
   // staging / workspace
   void* stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0};
-  void* d_out[2] = {nullptr, nullptr}; size_t out_cap[2] = {0, 0};
+  void* d_out = nullptr; size_t out_cap = 0;
   void* d_arr = nullptr; size_t arr_cap = 0;
   void* work = nullptr; size_t work_cap = 0;
   // options
@@ -169,6 +169,48 @@ struct Program {
     ++nsteps;
   }
 };
+
+// One unit of work of a call: a program with its per-parameter outputs, or (moments) the plain
+// mean / corrected standard deviation over all draws and chains of each parameter.
+struct Job {
+  Program pg;
+  bool moments = false;
+  void* out0 = nullptr;   // ess / mcse / mean
+  void* out1 = nullptr;   // rhat / std
+  void* arr = nullptr;    // per-element output of the transform calls
+};
+
+// Statistics.mean(x; dims=(1,2)) and Statistics.std(x; dims=(1,2)) (the quantities src/mcse.jl:50
+// uses), one CTA per parameter, two passes in double; NaN propagates.
+template <typename T>
+__global__ void __launch_bounds__(256) moments_kernel(const T* __restrict__ x, long long params, long long n,
+                                                     T* __restrict__ mean_out, T* __restrict__ std_out) {
+  __shared__ double red[8];
+  __shared__ double bc;
+  for (long long p = blockIdx.x; p < params; p += gridDim.x) {
+    const T* src = x + p * n;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) s += (double)__ldg(&src[i]);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int i = 0; i < 8; ++i) t += red[i]; bc = t / (double)n; }
+    __syncthreads();
+    const double m = bc;
+    double q = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) { const double d = (double)__ldg(&src[i]) - m; q = fma(d, d, q); }
+    q = warp_sum(q);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0; for (int i = 0; i < 8; ++i) t += red[i];
+      if (mean_out) mean_out[p] = (T)m;
+      if (std_out) std_out[p] = (T)sqrt(t / (double)(n - 1));
+    }
+    __syncthreads();
+  }
+}
 
 // log10(oftype(one(T), ntotal)) (src/ess_rhat.jl:514), correctly rounded: glibc's double
 // log10 is not (log10(40.0) is off by one ulp), so evaluate in long double and round once.
@@ -480,11 +522,25 @@ static int read_flags(mcd_ctx* ctx, unsigned* out) {
   return MCD_OK;
 }
 
-// Common driver: handles host staging (chunked, double-buffered, overlapped) or the
-// device-resident fast path, then surfaces kernel-raised flags.
+// Common driver: runs the jobs of one call over the same input.  Handles host staging (chunked,
+// double-buffered, overlapped: every chunk crosses PCIe once however many jobs read it) or
+// device-resident input, then surfaces kernel-raised flags.
 template <typename T>
-static int execute_t(mcd_ctx* ctx, const void* x, int mem, long long draws, long long chains, long long params,
-                     int split, Program& pg, void* ess_out, void* rhat_out, void* arr_out) {
+static int run_job(mcd_ctx* ctx, const Job& jb, const T* dx, long long params, const SplitGeom& g, T* o0, T* o1, void* arr) {
+  if (jb.moments) {
+    if (params == 0) return MCD_OK;
+    const int grid = (int)std::min<long long>(params, (long long)ctx->sm_count * 16);
+    moments_kernel<T><<<grid, 256, 0, ctx->stream>>>(dx, params, (long long)g.draws * g.chains, o0, o1);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    return MCD_OK;
+  }
+  return run_device<T>(ctx, dx, params, g, jb.pg, o0, o1, arr);
+}
+
+template <typename T>
+static int execute_jobs_t(mcd_ctx* ctx, const void* x, int mem, long long draws, long long chains, long long params,
+                          int split, Job* jobs, int njobs) {
   if (draws <= 0 || chains <= 0 || params < 0) return fail(ctx, MCD_EINVAL, "draws and chains must be positive");
   if (split < 1) return fail(ctx, MCD_EINVAL, "split_chains must be >= 1");
   if (draws * chains > (1ll << 30)) return fail(ctx, MCD_EUNSUPPORTED, "slab too large (draws*chains > 2^30)");
@@ -493,21 +549,25 @@ static int execute_t(mcd_ctx* ctx, const void* x, int mem, long long draws, long
   const long long n = g.n;
   CU(cudaSetDevice(ctx->device));
   CU(cudaMemsetAsync(ctx->d_flags, 0, sizeof(unsigned), ctx->stream));
-  if (pg.chain_inds) {
-    size_t bytes = (size_t)(pg.cps * pg.nsuper) * sizeof(int);
-    int rc = ensure_cap(ctx, (void**)&ctx->d_chain_inds, &ctx->chain_inds_cap, bytes);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(ctx->d_chain_inds, pg.chain_inds, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  bool can_raise = false;   // flags are only consulted for programs that can raise an error
+  for (int j = 0; j < njobs; ++j) {
+    const Program& pg = jobs[j].pg;
+    for (int s = 0; s < pg.nsteps; ++s) can_raise |= (pg.steps[s].transform == TR_IND_QUANTILE);
+    if (pg.chain_inds) {
+      size_t bytes = (size_t)(pg.cps * pg.nsuper) * sizeof(int);
+      int rc = ensure_cap(ctx, (void**)&ctx->d_chain_inds, &ctx->chain_inds_cap, bytes);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(ctx->d_chain_inds, pg.chain_inds, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
   }
   if (mem == MCD_DEVICE) {
-    int rc = run_device<T>(ctx, (const T*)x, params, g, pg, (T*)ess_out, (T*)rhat_out, arr_out);
-    if (rc) return rc;
-    // flags are only consulted for programs that can raise an error
-    bool can_raise = false;
-    for (int s = 0; s < pg.nsteps; ++s) can_raise |= (pg.steps[s].transform == TR_IND_QUANTILE);
+    for (int j = 0; j < njobs; ++j) {
+      int rc = run_job<T>(ctx, jobs[j], (const T*)x, params, g, (T*)jobs[j].out0, (T*)jobs[j].out1, jobs[j].arr);
+      if (rc) return rc;
+    }
     if (can_raise) {
       unsigned fl = 0;
-      rc = read_flags(ctx, &fl);
+      int rc = read_flags(ctx, &fl);
       if (rc) return rc;
       if (fl & FLAG_NAN_QUANTILE) return fail(ctx, MCD_ENAN, "quantiles are undefined in presence of NaNs");
     }
@@ -523,15 +583,17 @@ static int execute_t(mcd_ctx* ctx, const void* x, int mem, long long draws, long
   for (int i = 0; i < 2; ++i) {
     rc = ensure_cap(ctx, &ctx->stage[i], &ctx->stage_cap[i], (size_t)chunk * slab_bytes);
     if (rc) return rc;
-    rc = ensure_cap(ctx, &ctx->d_out[i], &ctx->out_cap[i], (size_t)std::max<long long>(params, 1) * sizeof(T));
+  }
+  const size_t col = (size_t)std::max<long long>(params, 1);   // device outputs: [job][2][params]
+  rc = ensure_cap(ctx, &ctx->d_out, &ctx->out_cap, (size_t)njobs * 2 * col * sizeof(T));
+  if (rc) return rc;
+  size_t arr_elem = 0;
+  for (int j = 0; j < njobs; ++j) if (jobs[j].pg.want_arr) arr_elem = std::max(arr_elem, (size_t)jobs[j].pg.arr_elem_bytes);
+  if (arr_elem) {
+    rc = ensure_cap(ctx, &ctx->d_arr, &ctx->arr_cap, (size_t)chunk * n * arr_elem);
     if (rc) return rc;
   }
-  if (pg.want_arr) {
-    rc = ensure_cap(ctx, &ctx->d_arr, &ctx->arr_cap, (size_t)chunk * n * pg.arr_elem_bytes);
-    if (rc) return rc;
-  }
-  T* d_ess = pg.want_ess ? (T*)ctx->d_out[0] : nullptr;
-  T* d_rhat = pg.want_rhat ? (T*)ctx->d_out[1] : nullptr;
+  T* dout = (T*)ctx->d_out;
   long long done = 0;
   int it = 0;
   while (done < params) {
@@ -543,26 +605,31 @@ static int execute_t(mcd_ctx* ctx, const void* x, int mem, long long draws, long
     ctx->h2d_bytes += cnt * (long long)slab_bytes;
     CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-    rc = run_device<T>(ctx, (const T*)ctx->stage[b], cnt, g, pg, d_ess ? d_ess + done : nullptr,
-                       d_rhat ? d_rhat + done : nullptr, pg.want_arr ? ctx->d_arr : nullptr);
-    if (rc) return rc;
-    if (pg.want_arr) {
-      size_t bytes = (size_t)cnt * n * pg.arr_elem_bytes;
-      CU(cudaMemcpyAsync((char*)arr_out + (size_t)done * n * pg.arr_elem_bytes, ctx->d_arr, bytes,
-                         cudaMemcpyDeviceToHost, ctx->stream));
-      ctx->d2h_bytes += (long long)bytes;
+    for (int j = 0; j < njobs; ++j) {
+      const Job& jb = jobs[j];
+      T* o0 = jb.out0 ? dout + (size_t)(2 * j) * col + done : nullptr;
+      T* o1 = jb.out1 ? dout + (size_t)(2 * j + 1) * col + done : nullptr;
+      rc = run_job<T>(ctx, jb, (const T*)ctx->stage[b], cnt, g, o0, o1, jb.pg.want_arr ? ctx->d_arr : nullptr);
+      if (rc) return rc;
+      if (jb.pg.want_arr) {
+        size_t bytes = (size_t)cnt * n * jb.pg.arr_elem_bytes;
+        CU(cudaMemcpyAsync((char*)jb.arr + (size_t)done * n * jb.pg.arr_elem_bytes, ctx->d_arr, bytes,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += (long long)bytes;
+      }
     }
     CU(cudaEventRecord(ctx->ev_done[b], ctx->stream));
     done += cnt;
     ++it;
   }
-  if (d_ess && ess_out) {
-    CU(cudaMemcpyAsync(ess_out, d_ess, (size_t)params * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->d2h_bytes += params * (long long)sizeof(T);
-  }
-  if (d_rhat && rhat_out) {
-    CU(cudaMemcpyAsync(rhat_out, d_rhat, (size_t)params * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->d2h_bytes += params * (long long)sizeof(T);
+  for (int j = 0; j < njobs; ++j) {
+    void* outs[2] = {jobs[j].out0, jobs[j].out1};
+    for (int h = 0; h < 2; ++h) {
+      if (!outs[h] || params == 0) continue;
+      CU(cudaMemcpyAsync(outs[h], dout + (size_t)(2 * j + h) * col, (size_t)params * sizeof(T), cudaMemcpyDeviceToHost,
+                         ctx->stream));
+      ctx->d2h_bytes += params * (long long)sizeof(T);
+    }
   }
   unsigned fl = 0;
   rc = read_flags(ctx, &fl);  // also synchronises the stream
@@ -571,11 +638,18 @@ static int execute_t(mcd_ctx* ctx, const void* x, int mem, long long draws, long
   return MCD_OK;
 }
 
+static int execute_jobs(mcd_ctx* ctx, const void* x, int mem, int dtype, long long draws, long long chains,
+                        long long params, int split, Job* jobs, int njobs) {
+  if (dtype == MCD_F64) return execute_jobs_t<double>(ctx, x, mem, draws, chains, params, split, jobs, njobs);
+  if (dtype == MCD_F32) return execute_jobs_t<float>(ctx, x, mem, draws, chains, params, split, jobs, njobs);
+  return fail(ctx, MCD_EINVAL, "bad dtype %d", dtype);
+}
+
 static int execute(mcd_ctx* ctx, const void* x, int mem, int dtype, long long draws, long long chains,
                    long long params, int split, Program& pg, void* ess_out, void* rhat_out, void* arr_out) {
-  if (dtype == MCD_F64) return execute_t<double>(ctx, x, mem, draws, chains, params, split, pg, ess_out, rhat_out, arr_out);
-  if (dtype == MCD_F32) return execute_t<float>(ctx, x, mem, draws, chains, params, split, pg, ess_out, rhat_out, arr_out);
-  return fail(ctx, MCD_EINVAL, "bad dtype %d", dtype);
+  Job jb;
+  jb.pg = pg; jb.out0 = pg.want_ess ? ess_out : nullptr; jb.out1 = pg.want_rhat ? rhat_out : nullptr; jb.arr = arr_out;
+  return execute_jobs(ctx, x, mem, dtype, draws, chains, params, split, &jb, 1);
 }
 
 // maxlag / niter rules of _ess_rhat(Val(:basic)) (src/ess_rhat.jl:469-484)
@@ -643,7 +717,7 @@ void mcd_destroy(mcd_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   void* ptrs[] = {ctx->ztab, ctx->tw, ctx->d_flags, ctx->d_chain_inds, ctx->d_redo, ctx->stage[0], ctx->stage[1],
-                  ctx->d_out[0], ctx->d_out[1], ctx->d_arr, ctx->work};
+                  ctx->d_out, ctx->d_arr, ctx->work};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
@@ -698,16 +772,10 @@ int64_t mcd_get_stat(const mcd_ctx* ctx, const char* key) {
   return -1;
 }
 
-int mcd_ess_rhat(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,
-                 int kind, int autocov_method, int split_chains, int maxlag, int relative, double tail_prob,
-                 int tail_prob_f64, void* ess_out, void* rhat_out) {
-  if (!ctx) return MCD_EINVAL;
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  ctx->err.clear();
-  if (!ess_out && !rhat_out) return fail(ctx, MCD_EINVAL, "both outputs are NULL");
+// Program of ess_rhat / ess / rhat for a Symbol kind (pg.want_ess / pg.want_rhat already set).
+static int build_ess_rhat(mcd_ctx* ctx, Program& pg, int dtype, int64_t draws, int kind, int autocov_method,
+                          int split_chains, int maxlag, int relative, double tail_prob, int tail_prob_f64) {
   if (kind < 0 || kind > 3) return fail(ctx, MCD_EINVAL, "the `kind` %d is not supported", kind);
-  Program pg;
-  pg.want_ess = ess_out != nullptr; pg.want_rhat = rhat_out != nullptr;
   if (pg.want_ess) { int rc = setup_ess(ctx, pg, draws, split_chains, autocov_method, maxlag, relative); if (rc) return rc; }
   const int rd = pg.want_ess ? RD_ESS_RHAT : RD_RHAT;
   const int p_f32 = (dtype == MCD_F32 && !tail_prob_f64) ? 1 : 0;
@@ -733,6 +801,20 @@ int mcd_ess_rhat(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws,
       pg.combine = CB_RANK;
       break;
   }
+  return MCD_OK;
+}
+
+int mcd_ess_rhat(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,
+                 int kind, int autocov_method, int split_chains, int maxlag, int relative, double tail_prob,
+                 int tail_prob_f64, void* ess_out, void* rhat_out) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->err.clear();
+  if (!ess_out && !rhat_out) return fail(ctx, MCD_EINVAL, "both outputs are NULL");
+  Program pg;
+  pg.want_ess = ess_out != nullptr; pg.want_rhat = rhat_out != nullptr;
+  int rc = build_ess_rhat(ctx, pg, dtype, draws, kind, autocov_method, split_chains, maxlag, relative, tail_prob, tail_prob_f64);
+  if (rc) return rc;
   return execute(ctx, x, mem, dtype, draws, chains, params, split_chains, pg, ess_out, rhat_out, nullptr);
 }
 
@@ -768,13 +850,9 @@ int mcd_ess_estimator(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t d
   return execute(ctx, x, mem, dtype, draws, chains, params, split_chains, pg, ess_out, nullptr, nullptr);
 }
 
-int mcd_mcse(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,
-             int estimator, double p, int p_f64, int autocov_method, int split_chains, int maxlag, void* mcse_out) {
-  if (!ctx) return MCD_EINVAL;
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  ctx->err.clear();
-  if (!mcse_out) return fail(ctx, MCD_EINVAL, "mcse_out is NULL");
-  Program pg;
+// Program of the ESS-based mcse rules (src/mcse.jl:45-118)
+static int build_mcse(mcd_ctx* ctx, Program& pg, int dtype, int64_t draws, int estimator, double p, int p_f64,
+                      int autocov_method, int split_chains, int maxlag) {
   pg.want_ess = true;
   int rc = setup_ess(ctx, pg, draws, split_chains, autocov_method, maxlag, 0);
   if (rc) return rc;
@@ -787,9 +865,66 @@ int mcd_mcse(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int
     default:
       return fail(ctx, MCD_EUNSUPPORTED, "mcse for estimator %d uses the subsampling bootstrap, which stays in the host language", estimator);
   }
-  rc = estimator_step(ctx, pg, estimator, p_f32 ? (double)(float)p : p, p_f32);
+  return estimator_step(ctx, pg, estimator, p_f32 ? (double)(float)p : p, p_f32);
+}
+
+int mcd_mcse(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,
+             int estimator, double p, int p_f64, int autocov_method, int split_chains, int maxlag, void* mcse_out) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->err.clear();
+  if (!mcse_out) return fail(ctx, MCD_EINVAL, "mcse_out is NULL");
+  Program pg;
+  int rc = build_mcse(ctx, pg, dtype, draws, estimator, p, p_f64, autocov_method, split_chains, maxlag);
   if (rc) return rc;
   return execute(ctx, x, mem, dtype, draws, chains, params, split_chains, pg, mcse_out, nullptr, nullptr);
+}
+
+// Fused per-parameter summary: what MCMCChains.summarystats / PosteriorStats.summarize ask of this
+// package for every parameter (mean, std, mcse(mean), mcse(std), ess(:bulk), ess(:tail),
+// rhat(:rank)), one call, the input staged (PCIe) once.  Each column equals the corresponding
+// reference call with the same keywords.
+int mcd_summary(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,
+                unsigned fields, int autocov_method, int split_chains, int maxlag, double tail_prob,
+                int tail_prob_f64, void* out) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->err.clear();
+  if (!out) return fail(ctx, MCD_EINVAL, "out is NULL");
+  if (fields == 0 || (fields & ~(unsigned)MCD_SUM_ALL)) return fail(ctx, MCD_EINVAL, "bad summary field mask 0x%x", fields);
+  if (dtype != MCD_F32 && dtype != MCD_F64) return fail(ctx, MCD_EINVAL, "bad dtype %d", dtype);
+  const size_t esz = dtype == MCD_F64 ? 8 : 4;
+  void* colp[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int ncol = 0;
+  for (int f = 0; f < 7; ++f)
+    if (fields & (1u << f)) colp[f] = (char*)out + (size_t)(ncol++) * (size_t)params * esz;
+  Job jobs[5];
+  int nj = 0, rc;
+  if (colp[0] || colp[1]) { Job& j = jobs[nj++]; j.moments = true; j.out0 = colp[0]; j.out1 = colp[1]; }
+  if (colp[2]) {
+    Job& j = jobs[nj++];
+    if ((rc = build_mcse(ctx, j.pg, dtype, draws, MCD_EST_MEAN, 0.0, 0, autocov_method, split_chains, maxlag))) return rc;
+    j.out0 = colp[2];
+  }
+  if (colp[3]) {
+    Job& j = jobs[nj++];
+    if ((rc = build_mcse(ctx, j.pg, dtype, draws, MCD_EST_STD, 0.0, 0, autocov_method, split_chains, maxlag))) return rc;
+    j.out0 = colp[3];
+  }
+  if (colp[4] || colp[6]) {
+    Job& j = jobs[nj++];
+    j.pg.want_ess = colp[4] != nullptr; j.pg.want_rhat = colp[6] != nullptr;
+    const int kind = j.pg.want_rhat ? MCD_KIND_RANK : MCD_KIND_BULK;   // ess(:rank) = ess(:bulk) (src/ess_rhat.jl:604-624)
+    if ((rc = build_ess_rhat(ctx, j.pg, dtype, draws, kind, autocov_method, split_chains, maxlag, 0, tail_prob, tail_prob_f64))) return rc;
+    j.out0 = colp[4]; j.out1 = colp[6];
+  }
+  if (colp[5]) {
+    Job& j = jobs[nj++];
+    j.pg.want_ess = true;
+    if ((rc = build_ess_rhat(ctx, j.pg, dtype, draws, MCD_KIND_TAIL, autocov_method, split_chains, maxlag, 0, tail_prob, tail_prob_f64))) return rc;
+    j.out0 = colp[5];
+  }
+  return execute_jobs(ctx, x, mem, dtype, draws, chains, params, split_chains, jobs, nj);
 }
 
 int mcd_rhat_nested(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,

@@ -17,6 +17,7 @@ using Statistics: Statistics
 using StatsBase: StatsBase
 
 export ess, ess_rhat, rhat, rhat_nested, mcse
+export summary_columns
 export AutocovMethod, FFTAutocovMethod, BDAAutocovMethod
 export ESSMethod, FFTESSMethod, BDAESSMethod
 
@@ -217,6 +218,38 @@ function mcse(samples::AbstractArray{<:Union{Missing,Real}}; kind=Statistics.mea
     (est === nothing || est[1] == 3) &&
         throw(ArgumentError("mcse for $kind uses the subsampling bootstrap of MCMCDiagnosticTools (src/mcse.jl:120-148)"))
     return _estimator_call(:mcd_mcse, samples, est; kwargs...)
+end
+
+const SUMMARY_FIELDS = (:mean, :std, :mcse_mean, :mcse_std, :ess_bulk, :ess_tail, :rhat)
+
+"""`summary_columns(samples; fields=SUMMARY_FIELDS, autocov_method, split_chains, maxlag, tail_prob)`: the
+per-parameter columns MCMCChains.summarystats / PosteriorStats.summarize assemble from separate calls
+(`mean`, `std`, `mcse(; kind=mean)`, `mcse(; kind=std)`, `ess(; kind=:bulk)`, `ess(; kind=:tail)`, `rhat(; kind=:rank)`)
+from ONE library call (`mcd_summary`): the host array crosses PCIe once.  Returns a NamedTuple of arrays."""
+function summary_columns(samples::AbstractArray{<:Union{Missing,Real}}; fields=SUMMARY_FIELDS,
+                         autocov_method::AbstractAutocovMethod=AutocovMethod(), split_chains::Int=2,
+                         maxlag::Int=250, tail_prob::Real=1//10)
+    all(f -> f in SUMMARY_FIELDS, fields) || throw(ArgumentError("unknown summary field in $fields"))
+    names = Tuple(f for f in SUMMARY_FIELDS if f in fields)
+    isempty(names) && throw(ArgumentError("no summary field requested"))
+    mask = UInt32(sum(1 << (findfirst(==(f), SUMMARY_FIELDS) - 1) for f in names))
+    T, dense, keep = _pack(samples)
+    niter = size(dense, 1) ÷ split_chains
+    if mask & 0x3c != 0
+        niter > 4 ? (maxlag > 0 || throw(DomainError(maxlag, "maxlag must be >0."))) :
+                    @warn "number of draws after splitting must be >4 but is $niter. ESS cannot be computed."
+    end
+    P = size(dense, 3)
+    out = Matrix{T}(undef, P, length(names))
+    tp, tp64 = _tailprob(tail_prob)
+    GC.@preserve dense out begin
+        rc = ccall((:mcd_summary, LIB), Cint,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Cuint, Cint, Cint, Cint, Cdouble, Cint, Ptr{Cvoid}),
+                   context(), dense, MCD_HOST, _dtype(T), size(dense, 1), size(dense, 2), P, mask,
+                   _code(autocov_method), split_chains, maxlag, tp, tp64, out)
+        _check(rc, maxlag)
+    end
+    return NamedTuple{names}(Tuple(_unpack(samples, T, out[:, i], keep) for i in eachindex(names)))
 end
 
 # `_validate_superchain_ids` + `unique_indices` (src/rhat_nested.jl:68-81, src/utils.jl:50-64)

@@ -637,6 +637,39 @@ def mcse(samples, kind="mean", **kw):
     raise NotImplementedError("SBM fallback (src/mcse.jl:120-148) is out of scope (SURVEY §2)")
 
 
+SUMMARY_FIELDS = ("mean", "std", "mcse_mean", "mcse_std", "ess_bulk", "ess_tail", "rhat")
+
+
+def summary(samples, fields=None, autocov_method=None, split_chains=2, maxlag=250, tail_prob=Fraction(1, 10)):
+    """The per-parameter columns downstream summaries assemble from separate calls of the
+    reference: every column is literally the reference call named beside it."""
+    x3, pshape = _as3d(samples)
+    T = _float_dtype(x3)
+    n = x3.shape[0] * x3.shape[1]
+    kw = dict(split_chains=split_chains, maxlag=maxlag)
+    if autocov_method is not None:
+        kw["autocov_method"] = autocov_method
+    names = SUMMARY_FIELDS if fields is None else tuple(fields)
+
+    def moments():
+        with np.errstate(all="ignore"):
+            xf = x3.astype(T)
+            m = (xf.sum(axis=(0, 1), dtype=T) / T(n)).astype(T)                   # Statistics.mean(x; dims=(1,2))
+            d = xf - m[None, None, :]
+            return m, np.sqrt(((d * d).sum(axis=(0, 1), dtype=T) / T(n - 1)).astype(T))  # Statistics.std
+
+    column = {
+        "mean": lambda: _restore(moments()[0], pshape),
+        "std": lambda: _restore(moments()[1], pshape),
+        "mcse_mean": lambda: mcse(samples, kind="mean", **kw),                    # src/mcse.jl:45-51
+        "mcse_std": lambda: mcse(samples, kind="std", **kw),                      # src/mcse.jl:52-65
+        "ess_bulk": lambda: ess(samples, kind="bulk", **kw),                      # src/ess_rhat.jl:604-624
+        "ess_tail": lambda: ess(samples, kind="tail", tail_prob=tail_prob, **kw), # src/ess_rhat.jl:298-311
+        "rhat": lambda: rhat(samples, kind="rank", split_chains=split_chains),    # src/ess_rhat.jl:410-420
+    }
+    return {k: column[k]() for k in SUMMARY_FIELDS if k in names}
+
+
 # ----------------------------------------------------------------------------------------
 # nested R-hat (src/rhat_nested.jl:43-188)
 # ----------------------------------------------------------------------------------------
