@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int niter = a.niter;
-  if (tid == 0) Khi[FAST_SENT] = 0xffffffffu;   // compares greater than every finite key, equal to none
+  if (tid == 0) { Khi[FAST_SENT] = 0xffffffffu; Khi[FAST_SENT + 1] = 0; }   // [SENT + 1]: work-list length
 
   for (long long param = blockIdx.x; param < a.params; param += gridDim.x) {
     const T* __restrict__ src = a.x + param * (long long)n + w * niter;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           for (int i = tid; i < FAST_WORDS / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(FC)[i] = make_uint4(0, 0, 0, 0);
           __syncthreads();
           unsigned bo[FAST_EPT];   // fine bucket | arrival offset << 16 ; later: packed rank info
-          unsigned maxoff = 0;
+          unsigned maxoff = 0, shared_mask = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
             if (lane + 32 * k < niter) {
@@ -213,59 +213,81 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
               Khi[st + off] = key_hi(x[k]);
               if (FastKeys<T>::TWO) Klo[st + off] = key_lo(x[k]);
             }
-            bo[k] = st | (c << 13);
+            bo[k] = st | (c << 12) | (off << 16);   // st <= 4095
+            shared_mask |= (c >= 2u ? 1u : 0u) << k;
           }
           __syncthreads();
-          // ---- resolve shared buckets (one fused loop: every round compares all 16 elements of the
-          // thread with the r-th member of their buckets; singletons and finished elements read the
-          // broadcast sentinel), finalise ranks, capture the median --------------------------------------
-          // order statistics to capture while the ranks are at hand
+          // ---- resolve shared buckets through a compacted work list (see mcd_fast.cuh); order
+          // statistics are captured while the ranks are at hand ------------------------------------
           const int ncap = pass == 0 ? a.ncap : (a.p1_red.src == FS_IND ? 2 : 0);
           const int cbase = pass == 0 ? 0 : 6;
           const int fmA = (n & 1) ? n / 2 : n / 2 - 1, fmB = n / 2;   // median positions (pass 1)
-          unsigned vhi[FAST_EPT], acc[FAST_EPT];
-          int cmx = 0;
+          unsigned* WL = FC;
+          unsigned short* RES = WP;
+          {
+            const unsigned mine = __popc(shared_mask);
+            unsigned incl = mine;
 #pragma unroll
-          for (int k = 0; k < FAST_EPT; ++k) {
-            const int c = (int)(bo[k] >> 13);
-            cmx = c > cmx ? c : cmx;
-            vhi[k] = key_hi(x[k]);
-            acc[k] = 0;
+            for (int o = 1; o < 32; o <<= 1) {
+              const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            unsigned base = 0;
+            if (lane == 31) base = atomicAdd(&Khi[FAST_SENT + 1], incl);
+            unsigned q = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+            const unsigned slot0 = (unsigned)tid << 20;
+            if (mine) {
+#pragma unroll
+              for (int k = 0; k < FAST_EPT; ++k)
+                if (shared_mask & (1u << k)) WL[q++] = bo[k] | (slot0 + ((unsigned)k << 28));   // slot = k * 256 + tid
+            }
           }
-          const int trip = __reduce_max_sync(0xffffffffu, cmx >= 2 ? cmx : 0);
-          for (int r = 0; r < trip; ++r) {
+          __syncthreads();
+          {
+            const unsigned listn = Khi[FAST_SENT + 1];
+            for (unsigned q = tid; q < listn; q += FAST_THREADS) {
+              const unsigned it = WL[q];
+              const unsigned st = it & 0xfffu, c = (it >> 12) & 15u, off = (it >> 16) & 15u;
+              const unsigned vhi = Khi[st + off];
+              const unsigned vlo = FastKeys<T>::TWO ? Klo[st + off] : 0u;
+              unsigned less = 0, eq = 0;
+              for (unsigned j = st; j < st + c; ++j) {
+                const unsigned yhi = Khi[j];
+                if (yhi < vhi) ++less;
+                else if (yhi == vhi) {
+                  if constexpr (FastKeys<T>::TWO) { const unsigned ylo = Klo[j]; less += ylo < vlo; eq += ylo == vlo; }
+                  else ++eq;
+                }
+              }
+              const int lo = (int)(st + less), hi = lo + (int)eq;
+              for (int ci = 0; ci < ncap; ++ci) {
+                const int cp = pass == 0 ? a.cap_pos[ci] : (ci == 0 ? fmA : fmB);
+                if (lo <= cp && cp < hi) {
+                  if constexpr (FastKeys<T>::TWO) cap[cbase + ci] = key_value(((unsigned long long)vhi << 32) | vlo);
+                  else cap[cbase + ci] = (double)key_value(vhi);
+                }
+              }
+              const unsigned zi = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
+              RES[it >> 20] = (unsigned short)((zi >> 1) + ((zi & 1u) ? (unsigned)n : 0u));   // split z table
+            }
+          }
+          __syncthreads();
+          if (tid == 0) Khi[FAST_SENT + 1] = 0;
+          if (ncap > 0) {
 #pragma unroll
             for (int k = 0; k < FAST_EPT; ++k) {
-              const unsigned st = bo[k] & 0x1fffu, c = bo[k] >> 13;
-              const unsigned ce = c >= 2u ? c : 0u;
-              const unsigned yhi = Khi[(unsigned)r < ce ? st + (unsigned)r : (unsigned)FAST_SENT];
-              acc[k] += (unsigned)(yhi < vhi[k]) + ((unsigned)(yhi == vhi[k]) << 16);
-            }
-          }
-          unsigned anytie = 0;
-#pragma unroll
-          for (int k = 0; k < FAST_EPT; ++k) anytie |= (acc[k] >> 17);   // eqc >= 2
-          const bool slow = __any_sync(0xffffffffu, anytie != 0);
-#pragma unroll
-          for (int k = 0; k < FAST_EPT; ++k) {
-            const bool valid = lane + 32 * k < niter;
-            const int st = (int)(bo[k] & 0x1fffu), c = (int)(bo[k] >> 13);
-            int less = (int)(acc[k] & 0xffffu), eq = 1;
-            if (slow && (acc[k] >> 17)) {   // another member shares the hi word: exact comparison on (hi, lo)
-              const unsigned le = resolve_exact<FastKeys<T>::TWO>(Khi, Klo, st, c, vhi[k], key_lo(x[k]));
-              less = (int)(le & 0xffffu); eq = (int)(le >> 16);
-            }
-            const int lo = st + less, hi = lo + eq;
-            if (valid) {
-#pragma unroll
-              for (int c = 0; c < 6; ++c) {
-                const int cp = pass == 0 ? a.cap_pos[c] : (c == 0 ? fmA : fmB);
-                if (c < ncap && lo <= cp && cp < hi) cap[cbase + c] = (double)x[k];
+              const int st = (int)(bo[k] & 0xfffu);
+              if (lane + 32 * k < niter && !(shared_mask & (1u << k))) {
+                for (int ci = 0; ci < ncap; ++ci) {
+                  const int cp = pass == 0 ? a.cap_pos[ci] : (ci == 0 ? fmA : fmB);
+                  if (st == cp) cap[cbase + ci] = (double)x[k];
+                }
               }
             }
-            const unsigned zi = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
-            bo[k] = (zi >> 1) + ((zi & 1u) ? (unsigned)n : 0u);   // split z table: integer ranks first
           }
+#pragma unroll
+          for (int k = 0; k < FAST_EPT; ++k)
+            bo[k] = (shared_mask & (1u << k)) ? (unsigned)RES[k * FAST_THREADS + tid] : (bo[k] & 0xfffu);
           if (first_is_rankz) {
 #pragma unroll
             for (int k = 0; k < FAST_EPT; ++k) z[k] = (lane + 32 * k < niter) ? __ldg(&a.ztab[bo[k]]) : (T)0;
