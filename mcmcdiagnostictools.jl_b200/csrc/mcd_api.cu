@@ -172,8 +172,10 @@ struct Program {
 
 // One unit of work of a call: a program with its per-parameter outputs, or (moments) the plain
 // mean / corrected standard deviation over all draws and chains of each parameter.
+enum JobRole { ROLE_NONE = 0, ROLE_MOMENTS, ROLE_MCSE_MEAN, ROLE_MCSE_STD, ROLE_BULK_RHAT, ROLE_TAIL };
 struct Job {
   Program pg;
+  int role = ROLE_NONE;   // set by mcd_summary: lets the driver fuse the jobs into one kernel
   bool moments = false;
   void* out0 = nullptr;   // ess / mcse / mean
   void* out1 = nullptr;   // rhat / std
@@ -365,6 +367,31 @@ static int run_slab(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
 }
 
 // The register-resident fast kernel (mcd_fast.cuh) for 8 split chains of <= 512 draws.
+// type-7 quantile position and weight (Statistics.quantile, call site src/ess_rhat.jl:655): the two
+// order statistics to capture (slots slot, slot + 1) and the threshold built from them
+template <typename T>
+static void plan_quantile(FastGenArgs<T>& a, int n, double p, int f32, int slot, int thr_index) {
+  long long j; double gq;
+  if (f32) {
+    const float pf = (float)p, mm = (float)(1.0 - (double)pf);
+    const float aleph = std::fmaf((float)n, pf, mm);
+    j = (long long)std::trunc(aleph);
+    j = std::min<long long>(std::max<long long>(j, 1), n - 1);
+    float gf = aleph - (float)j;
+    gf = gf < 0.f ? 0.f : (gf > 1.f ? 1.f : gf);
+    gq = (double)gf;
+  } else {
+    const double aleph = std::fma((double)n, p, 1.0 - p);
+    j = (long long)std::trunc(aleph);
+    j = std::min<long long>(std::max<long long>(j, 1), n - 1);
+    gq = aleph - (double)j;
+    gq = gq < 0.0 ? 0.0 : (gq > 1.0 ? 1.0 : gq);
+  }
+  a.cap_pos[slot] = (int)(j - 1); a.cap_pos[slot + 1] = (int)j;
+  a.thr[thr_index].quantile = 1; a.thr[thr_index].capA = slot; a.thr[thr_index].capB = slot + 1;
+  a.thr[thr_index].f32 = f32; a.thr[thr_index].g = gq;
+}
+
 template <typename T>
 static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom& g, const Program& pg,
                     T* d_ess, T* d_rhat, bool* handled) {
@@ -394,34 +421,13 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   const int n = g.n;
   const int mA = (n & 1) ? n / 2 : n / 2 - 1, mB = n / 2;
   a.cap_pos[0] = mA; a.cap_pos[1] = mB;
-  // type-7 quantile position and weight (Statistics.quantile, call site src/ess_rhat.jl:655)
-  auto quantile_plan = [&](double p, int f32, int slot, int thr_index) {
-    long long j; double gq;
-    if (f32) {
-      const float pf = (float)p, mm = (float)(1.0 - (double)pf);
-      const float aleph = std::fmaf((float)n, pf, mm);
-      j = (long long)std::trunc(aleph);
-      j = std::min<long long>(std::max<long long>(j, 1), n - 1);
-      float gf = aleph - (float)j;
-      gf = gf < 0.f ? 0.f : (gf > 1.f ? 1.f : gf);
-      gq = (double)gf;
-    } else {
-      const double aleph = std::fma((double)n, p, 1.0 - p);
-      j = (long long)std::trunc(aleph);
-      j = std::min<long long>(std::max<long long>(j, 1), n - 1);
-      gq = aleph - (double)j;
-      gq = gq < 0.0 ? 0.0 : (gq > 1.0 ? 1.0 : gq);
-    }
-    a.cap_pos[slot] = (int)(j - 1); a.cap_pos[slot + 1] = (int)j;
-    a.thr[thr_index].quantile = 1; a.thr[thr_index].capA = slot; a.thr[thr_index].capB = slot + 1;
-    a.thr[thr_index].f32 = f32; a.thr[thr_index].g = gq;
-  };
+  auto quantile_plan = [&](double p, int f32, int slot, int thr_index) { plan_quantile<T>(a, n, p, f32, slot, thr_index); };
   auto ind_red = [&](int i, int thr_index) { a.p0_red[i].src = FS_IND; a.p0_red[i].want_ess = 1; a.p0_red[i].thr = thr_index; };
   const bool plain1 = pg.nsteps == 1 && pg.combine == CB_PLAIN;
   if (pg.nsteps == 1 && pg.combine == CB_MCSE_MEAN && s0.transform == TR_NONE && s0.reduce == RD_ESS_RHAT) {
-    a.p0_nred = 1; a.p0_red[0].src = FS_X; a.p0_red[0].want_ess = 1; a.ess_mode = 1; a.mcse_mode = 1;
+    a.p0_nred = 1; a.p0_red[0].src = FS_X; a.p0_red[0].want_ess = 1; a.ess_mode = 1; a.mcse_mode = 1; a.need_side = 1;
   } else if (pg.nsteps == 1 && pg.combine == CB_MCSE_STD && s0.transform == TR_STDPROXY && s0.reduce == RD_ESS_RHAT) {
-    a.p0_nred = 1; a.p0_red[0].src = FS_SQDEV; a.p0_red[0].want_ess = 1; a.ess_mode = 1; a.mcse_mode = 2;
+    a.p0_nred = 1; a.p0_red[0].src = FS_SQDEV; a.p0_red[0].want_ess = 1; a.ess_mode = 1; a.mcse_mode = 2; a.need_side = 1;
   } else if ((pg.combine == CB_TAIL && pg.nsteps == 3) || (pg.combine == CB_TAIL_ESS && pg.nsteps == 2)) {
     // _ess(Val(:tail)): min of the two quantile-indicator ESS (src/ess_rhat.jl:301-311) [+ tail R-hat]
     if (s0.transform != TR_IND_QUANTILE || pg.steps[1].transform != TR_IND_QUANTILE) return MCD_OK;
@@ -440,7 +446,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
     a.p0_rank = 1; a.ncap = 4; a.nthr = 1; quantile_plan(s0.p, s0.p_f32, 2, 0);
     a.p0_nred = 1; ind_red(0, 0); a.ess_mode = 1;
   } else if (plain1 && s0.reduce == RD_ESS_RHAT && !pg.want_rhat && s0.transform == TR_STDPROXY) {
-    a.p0_nred = 1; a.p0_red[0].src = FS_SQDEV; a.p0_red[0].want_ess = 1; a.ess_mode = 1;
+    a.p0_nred = 1; a.p0_red[0].src = FS_SQDEV; a.p0_red[0].want_ess = 1; a.ess_mode = 1; a.need_side = 1;
   } else if (plain1 && s0.reduce == RD_ESS_RHAT && !pg.want_rhat && s0.transform == TR_FOLD_IND_MEDIAN) {
     a.p0_rank = 1; a.ncap = 2; a.do_fold = 1; a.p1_red.src = FS_IND; a.p1_red.want_ess = 1; a.ess_mode = 4;
   } else return MCD_OK;
@@ -466,7 +472,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
     const unsigned grid = ctx->fast_grid_mult ? (unsigned)std::min<long long>(params, (long long)ctx->fast_grid_mult * 2 * ctx->sm_count) : (unsigned)params;
     kern<<<grid, FAST_THREADS, smem, ctx->stream>>>(a);
   } else {
-    const size_t smem = fast_smem_bytes<T>(pg.maxlag) + 16 * 8 + (size_t)ctx->fast_pad_smem;
+    const size_t smem = fast_smem_bytes<T>(pg.maxlag) + FASTGEN_EXTRA_SMEM + (size_t)ctx->fast_pad_smem;
     auto kern = fastgen_kernel<T>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(ga);
@@ -478,6 +484,91 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   rc = run_slab<T>(ctx, dx, params, g, pg, d_ess, d_rhat, nullptr, &h2, ctx->d_redo + 1, ctx->d_redo);
   if (rc) return rc;
   if (!h2) return fail(ctx, MCD_EUNSUPPORTED, "internal: redo kernel unavailable");
+  ctx->last_path = 3;
+  *handled = true;
+  return MCD_OK;
+}
+
+// The jobs of mcd_summary in ONE launch of the register-resident kernel (8 split chains of <= 512
+// draws, direct autocovariance): x is read from HBM once and ranked twice (raw, folded) for all
+// seven columns.  o[j][0..1] are the device outputs of job j.
+template <typename T>
+static int run_fast_summary(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom& g, const Job* jobs, int njobs,
+                            T* const (*o)[2], bool* handled) {
+  *handled = false;
+  if (g.nch != FAST_NCH || g.rem != 0 || g.niter < 2 || g.niter > FAST_MAXITER || params >= (1ll << 31) || params == 0) return MCD_OK;
+  FastGenArgs<T> a;
+  memset(&a, 0, sizeof a);
+  a.sum_mode = 1; a.need_side = 1;
+  a.s_bulk = a.s_tlo = a.s_thi = a.s_mean = a.s_std = -1;
+  const int n = g.n;
+  a.cap_pos[0] = (n & 1) ? n / 2 : n / 2 - 1; a.cap_pos[1] = n / 2;
+  const Program* ess_pg = nullptr;
+  int bulk = -1, tail = -1, mm = -1, ms = -1, mom = -1;
+  for (int j = 0; j < njobs; ++j) {
+    switch (jobs[j].role) {
+      case ROLE_MOMENTS: mom = j; break;
+      case ROLE_MCSE_MEAN: mm = j; break;
+      case ROLE_MCSE_STD: ms = j; break;
+      case ROLE_BULK_RHAT: bulk = j; break;
+      case ROLE_TAIL: tail = j; break;
+      default: return MCD_OK;
+    }
+    if (jobs[j].role != ROLE_MOMENTS && jobs[j].pg.want_ess) {
+      if (!jobs[j].pg.ess_nan && jobs[j].pg.method != MCD_AUTOCOV_DIRECT) return MCD_OK;
+      ess_pg = &jobs[j].pg;
+    }
+  }
+  if (bulk < 0 && tail < 0 && mm < 0 && ms < 0) return MCD_OK;   // moments alone: the plain kernel is HBM-bound already
+  int nred = 0;
+  if (bulk >= 0) {   // must be the first reduction of its pass (FS_RANKZ)
+    a.p0_rank = 1; a.s_bulk = nred;
+    a.p0_red[nred].src = FS_RANKZ; a.p0_red[nred].want_ess = jobs[bulk].pg.want_ess ? 1 : 0; ++nred;
+    a.col[4] = o[bulk][0];
+    if (jobs[bulk].pg.want_rhat) { a.col[6] = o[bulk][1]; a.do_fold = 1; a.p1_red.src = FS_RANKZ; }
+  }
+  if (tail >= 0) {
+    const Program& pg = jobs[tail].pg;
+    if (pg.nsteps != 2 || pg.steps[0].transform != TR_IND_QUANTILE || pg.steps[1].transform != TR_IND_QUANTILE) return MCD_OK;
+    a.p0_rank = 1; a.ncap = 6; a.nthr = 2;
+    plan_quantile<T>(a, n, pg.steps[0].p, pg.steps[0].p_f32, 2, 0);
+    plan_quantile<T>(a, n, pg.steps[1].p, pg.steps[1].p_f32, 4, 1);
+    a.s_tlo = nred; a.p0_red[nred].src = FS_IND; a.p0_red[nred].want_ess = 1; a.p0_red[nred].thr = 0; ++nred;
+    a.s_thi = nred; a.p0_red[nred].src = FS_IND; a.p0_red[nred].want_ess = 1; a.p0_red[nred].thr = 1; ++nred;
+    a.col[5] = o[tail][0];
+  }
+  if (mm >= 0) { a.s_mean = nred; a.p0_red[nred].src = FS_X; a.p0_red[nred].want_ess = 1; ++nred; a.col[2] = o[mm][0]; }
+  if (ms >= 0) { a.s_std = nred; a.p0_red[nred].src = FS_SQDEV; a.p0_red[nred].want_ess = 1; ++nred; a.col[3] = o[ms][0]; }
+  if (a.do_fold && !a.ncap) a.ncap = 2;   // the fold needs the median of x
+  a.p0_nred = nred;
+  if (mom >= 0) { a.col[0] = o[mom][0]; a.col[1] = o[mom][1]; }
+  a.x = dx; a.params = params; a.niter = g.niter;
+  a.maxlag = ess_pg ? ess_pg->maxlag : 1; a.relative = 0; a.ess_nan = ess_pg ? ess_pg->ess_nan : 1;
+  a.rel_ess_max = rel_ess_max_of<T>((long long)g.niter * g.nch);
+  const int dtype = sizeof(T) == 8 ? MCD_F64 : MCD_F32;
+  if (a.p0_rank || a.do_fold) {
+    int rc = ensure_ztab(ctx, dtype, g.n);
+    if (rc) return rc;
+    a.ztab = (const T*)ctx->ztab + 2 * (size_t)g.n;   // split layout
+  }
+  int rc = ensure_cap(ctx, (void**)&ctx->d_redo, &ctx->redo_cap, (size_t)(params + 1) * sizeof(int));
+  if (rc) return rc;
+  a.redo_count = ctx->d_redo; a.redo_list = ctx->d_redo + 1;
+  CU(cudaMemsetAsync(ctx->d_redo, 0, sizeof(int), ctx->stream));
+  const size_t smem = fast_smem_bytes<T>(a.maxlag) + FASTGEN_EXTRA_SMEM + (size_t)ctx->fast_pad_smem;
+  auto kern = fastgen_kernel<T>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  // slabs the kernel declined (NaN, infinite range, heavy ties): every program again on the general kernel
+  for (int j = 0; j < njobs; ++j) {
+    if (jobs[j].role == ROLE_MOMENTS) continue;
+    bool h2 = false;
+    rc = run_slab<T>(ctx, dx, params, g, jobs[j].pg, o[j][0], o[j][1], nullptr, &h2, ctx->d_redo + 1, ctx->d_redo);
+    if (rc) return rc;
+    if (!h2) return fail(ctx, MCD_EUNSUPPORTED, "internal: redo kernel unavailable");
+  }
   ctx->last_path = 3;
   *handled = true;
   return MCD_OK;
@@ -538,6 +629,24 @@ static int run_job(mcd_ctx* ctx, const Job& jb, const T* dx, long long params, c
   return run_device<T>(ctx, dx, params, g, jb.pg, o0, o1, arr);
 }
 
+// All jobs of a call on one device-resident chunk (fused into one kernel when they are the
+// columns of mcd_summary on a fast-kernel shape).
+template <typename T>
+static int run_jobs(mcd_ctx* ctx, const Job* jobs, int njobs, const T* dx, long long params, const SplitGeom& g,
+                    T* const (*o)[2], void* const* arrs) {
+  if (njobs > 1 && ctx->force_path == 0) {
+    bool handled = false;
+    int rc = run_fast_summary<T>(ctx, dx, params, g, jobs, njobs, o, &handled);
+    if (rc) return rc;
+    if (handled) return MCD_OK;
+  }
+  for (int j = 0; j < njobs; ++j) {
+    int rc = run_job<T>(ctx, jobs[j], dx, params, g, o[j][0], o[j][1], arrs[j]);
+    if (rc) return rc;
+  }
+  return MCD_OK;
+}
+
 template <typename T>
 static int execute_jobs_t(mcd_ctx* ctx, const void* x, int mem, long long draws, long long chains, long long params,
                           int split, Job* jobs, int njobs) {
@@ -561,8 +670,10 @@ static int execute_jobs_t(mcd_ctx* ctx, const void* x, int mem, long long draws,
     }
   }
   if (mem == MCD_DEVICE) {
-    for (int j = 0; j < njobs; ++j) {
-      int rc = run_job<T>(ctx, jobs[j], (const T*)x, params, g, (T*)jobs[j].out0, (T*)jobs[j].out1, jobs[j].arr);
+    {
+      T* o[8][2]; void* arrs[8];
+      for (int j = 0; j < njobs; ++j) { o[j][0] = (T*)jobs[j].out0; o[j][1] = (T*)jobs[j].out1; arrs[j] = jobs[j].arr; }
+      int rc = run_jobs<T>(ctx, jobs, njobs, (const T*)x, params, g, o, arrs);
       if (rc) return rc;
     }
     if (can_raise) {
@@ -605,12 +716,16 @@ static int execute_jobs_t(mcd_ctx* ctx, const void* x, int mem, long long draws,
     ctx->h2d_bytes += cnt * (long long)slab_bytes;
     CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+    T* o[8][2]; void* arrs[8];
+    for (int j = 0; j < njobs; ++j) {
+      o[j][0] = jobs[j].out0 ? dout + (size_t)(2 * j) * col + done : nullptr;
+      o[j][1] = jobs[j].out1 ? dout + (size_t)(2 * j + 1) * col + done : nullptr;
+      arrs[j] = jobs[j].pg.want_arr ? ctx->d_arr : nullptr;
+    }
+    rc = run_jobs<T>(ctx, jobs, njobs, (const T*)ctx->stage[b], cnt, g, o, arrs);
+    if (rc) return rc;
     for (int j = 0; j < njobs; ++j) {
       const Job& jb = jobs[j];
-      T* o0 = jb.out0 ? dout + (size_t)(2 * j) * col + done : nullptr;
-      T* o1 = jb.out1 ? dout + (size_t)(2 * j + 1) * col + done : nullptr;
-      rc = run_job<T>(ctx, jb, (const T*)ctx->stage[b], cnt, g, o0, o1, jb.pg.want_arr ? ctx->d_arr : nullptr);
-      if (rc) return rc;
       if (jb.pg.want_arr) {
         size_t bytes = (size_t)cnt * n * jb.pg.arr_elem_bytes;
         CU(cudaMemcpyAsync((char*)jb.arr + (size_t)done * n * jb.pg.arr_elem_bytes, ctx->d_arr, bytes,
@@ -900,29 +1015,29 @@ int mcd_summary(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, 
     if (fields & (1u << f)) colp[f] = (char*)out + (size_t)(ncol++) * (size_t)params * esz;
   Job jobs[5];
   int nj = 0, rc;
-  if (colp[0] || colp[1]) { Job& j = jobs[nj++]; j.moments = true; j.out0 = colp[0]; j.out1 = colp[1]; }
+  if (colp[0] || colp[1]) { Job& j = jobs[nj++]; j.moments = true; j.role = ROLE_MOMENTS; j.out0 = colp[0]; j.out1 = colp[1]; }
   if (colp[2]) {
     Job& j = jobs[nj++];
     if ((rc = build_mcse(ctx, j.pg, dtype, draws, MCD_EST_MEAN, 0.0, 0, autocov_method, split_chains, maxlag))) return rc;
-    j.out0 = colp[2];
+    j.out0 = colp[2]; j.role = ROLE_MCSE_MEAN;
   }
   if (colp[3]) {
     Job& j = jobs[nj++];
     if ((rc = build_mcse(ctx, j.pg, dtype, draws, MCD_EST_STD, 0.0, 0, autocov_method, split_chains, maxlag))) return rc;
-    j.out0 = colp[3];
+    j.out0 = colp[3]; j.role = ROLE_MCSE_STD;
   }
   if (colp[4] || colp[6]) {
     Job& j = jobs[nj++];
     j.pg.want_ess = colp[4] != nullptr; j.pg.want_rhat = colp[6] != nullptr;
     const int kind = j.pg.want_rhat ? MCD_KIND_RANK : MCD_KIND_BULK;   // ess(:rank) = ess(:bulk) (src/ess_rhat.jl:604-624)
     if ((rc = build_ess_rhat(ctx, j.pg, dtype, draws, kind, autocov_method, split_chains, maxlag, 0, tail_prob, tail_prob_f64))) return rc;
-    j.out0 = colp[4]; j.out1 = colp[6];
+    j.out0 = colp[4]; j.out1 = colp[6]; j.role = ROLE_BULK_RHAT;
   }
   if (colp[5]) {
     Job& j = jobs[nj++];
     j.pg.want_ess = true;
     if ((rc = build_ess_rhat(ctx, j.pg, dtype, draws, MCD_KIND_TAIL, autocov_method, split_chains, maxlag, 0, tail_prob, tail_prob_f64))) return rc;
-    j.out0 = colp[5];
+    j.out0 = colp[5]; j.role = ROLE_TAIL;
   }
   return execute_jobs(ctx, x, mem, dtype, draws, chains, params, split_chains, jobs, nj);
 }

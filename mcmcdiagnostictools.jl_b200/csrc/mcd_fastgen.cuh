@@ -27,23 +27,31 @@ struct FastRed { int src, want_ess, thr; };
 // threshold from captured order statistics: median a/2 + b/2, or type-7 quantile a + g (b - a)
 struct FastThr { int quantile, capA, capB, f32; double g; };
 
+constexpr int FASTGEN_EXTRA_SMEM = 24 * 8;   // cap[8] + thrv[4] + res[12] + side[4] replace the lean kernel's thr[4]
+
 template <typename T> struct FastGenArgs {
   const T* x;
   long long params;
   int niter;            // draws per split chain; n = 8 * niter
   // pass 0 works on x, pass 1 (do_fold) on |x - median(x)|
   int p0_rank;          // pass 0 needs the ranks of x (for z, or for order statistics)
-  int p0_nred;          // reductions on pass-0 data -> result slots 0..2
-  FastRed p0_red[3];
+  int p0_nred;          // reductions on pass-0 data -> result slots 0..4
+  FastRed p0_red[5];
   int ncap;             // order statistics of x to capture: sorted positions (0-based) -> cap[0..ncap)
   int cap_pos[6];       // when do_fold: cap_pos[0], cap_pos[1] must be the two median positions
   int nthr;             // thresholds computed from the captures -> thrv[0..nthr)
   FastThr thr[3];
   int do_fold;
-  FastRed p1_red;       // reduction on the folded data -> result slot 3 (FS_IND uses the median of the folded values)
-  int ess_mode;         // 0 none, 1 slot 0, 2 min(slot 0, slot 1), 4 slot 3
-  int rhat_mode;        // 0 none, 1 slot 0, 2 slot 3, 3 max(slot 3, slot 0)
+  FastRed p1_red;       // reduction on the folded data -> result slot 5 (FS_IND uses the median of the folded values)
+  int ess_mode;         // 0 none, 1 slot 0, 2 min(slot 0, slot 1), 4 slot 5
+  int rhat_mode;        // 0 none, 1 slot 0, 2 slot 5, 3 max(slot 5, slot 0)
   int mcse_mode;        // 0 none, 1 mean: std(x)/sqrt(ess) (mcse.jl:45-51), 2 std: sqrt((m4/m2 - m2)/ess)/2 (mcse.jl:52-65)
+  int need_side;        // mean / std / m2 / m4 over all draws and chains (mcse rules, FS_SQDEV, summary)
+  // fused summary (mcd_summary): columns mean, std, mcse_mean, mcse_std, ess_bulk, ess_tail, rhat
+  // (null = not requested); s_* = result slot of the reduction feeding a column (-1 = absent)
+  int sum_mode;
+  int s_bulk, s_tlo, s_thi, s_mean, s_std;
+  T* col[7];
   int maxlag, relative, ess_nan;
   T rel_ess_max;
   T* ess_out;
@@ -70,8 +78,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
   double* wred = part + 64;                                // [2][8]
   double* cap = wred + 16;                                 // [8] captured order statistics (6,7: folded median)
   double* thrv = cap + 8;                                  // [4] thresholds (3: median of the folded values)
-  double* res = thrv + 4;                                  // [8] ess[4], rhat[4] per result slot
-  int* iflag = reinterpret_cast<int*>(res + 8);            // [8] warp totals / flags
+  double* res = thrv + 4;                                  // [12] ess[6], rhat[6] per result slot
+  double* side = res + 12;                                 // [4] mean, std, mean(proxy), mean(proxy^2) over the slab
+  int* iflag = reinterpret_cast<int*>(side + 4);           // [8] warp totals / flags
   int* woffx = iflag + 8;                                  // [8] exclusive warp offsets
   T* gamma = reinterpret_cast<T*>(woffx + 8);              // [maxlag + 9]
 
@@ -89,6 +98,41 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
     }
     bool redo = false;
     T vmin = (T)0, vmax = (T)0;
+    // statistics over all draws x chains (Statistics.mean / std with dims=(1,2); src/mcse.jl:50,56,62-63)
+    if (a.need_side) {
+      auto block_total = [&](double v) -> double {
+        v = warp_sum(v);
+        __syncthreads();
+        if (lane == 0) wred[w] = v;
+        __syncthreads();
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < FAST_NCH; ++i) t += wred[i];
+        return t;
+      };
+      double sx = 0.0;
+#pragma unroll
+      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) sx += (double)x[k];
+      const T mean_all = (T)(block_total(sx) / (double)n);
+      double s2 = 0.0, s4 = 0.0;
+#pragma unroll
+      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) {
+        const T d = x[k] - mean_all;
+        const T pz = d * d;
+        s2 += (double)pz;
+        s4 = fma((double)pz, (double)pz, s4);
+      }
+      const double t2 = block_total(s2), t4 = block_total(s4);
+      if (tid == 0) {
+        const T sd = sqrt((T)(t2 / (double)(n - 1)));          // std(x; corrected)
+        side[0] = (double)mean_all; side[1] = (double)sd;
+        side[2] = (double)(T)(t2 / (double)n); side[3] = (double)(T)(t4 / (double)n);   // mean(proxy), mean(proxy^2)
+        if (a.sum_mode) {
+          if (a.col[0]) a.col[0][param] = mean_all;
+          if (a.col[1]) a.col[1][param] = sd;
+        }
+      }
+    }
 
     for (int pass = 0; pass < 2; ++pass) {
       if (pass == 1 && !a.do_fold) break;
@@ -224,6 +268,20 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           const int fmA = (n & 1) ? n / 2 : n / 2 - 1, fmB = n / 2;   // median positions (pass 1)
           unsigned* WL = FC;
           unsigned short* RES = WP;
+          // WANT[pos] = mask of the captures that ask for sorted position pos (second half of the dead prefixes)
+          unsigned char* WANT = reinterpret_cast<unsigned char*>(WP) + 2 * FAST_NMAX;
+          if (ncap > 0 && w == 0) {
+#pragma unroll
+            for (int i = 0; i < FAST_NMAX / (16 * 32); ++i) reinterpret_cast<uint4*>(WANT)[lane + 32 * i] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+              for (int ci = 0; ci < 6; ++ci) {
+                const int cp = pass == 0 ? a.cap_pos[ci] : (ci == 0 ? fmA : fmB);
+                if (ci < ncap) WANT[cp] |= (unsigned char)(1u << ci);
+              }
+            }
+          }
           {
             const unsigned mine = __popc(shared_mask);
             unsigned incl = mine;
@@ -260,11 +318,14 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
                 }
               }
               const int lo = (int)(st + less), hi = lo + (int)eq;
-              for (int ci = 0; ci < ncap; ++ci) {
-                const int cp = pass == 0 ? a.cap_pos[ci] : (ci == 0 ? fmA : fmB);
-                if (lo <= cp && cp < hi) {
-                  if constexpr (FastKeys<T>::TWO) cap[cbase + ci] = key_value(((unsigned long long)vhi << 32) | vlo);
-                  else cap[cbase + ci] = (double)key_value(vhi);
+              if (ncap > 0) {
+                unsigned m = 0;
+                for (int pos = lo; pos < hi; ++pos) m |= WANT[pos];
+                if (m) {
+                  double v;
+                  if constexpr (FastKeys<T>::TWO) v = key_value(((unsigned long long)vhi << 32) | vlo);
+                  else v = (double)key_value(vhi);
+                  for (int ci = 0; ci < 6; ++ci) if (m & (1u << ci)) cap[cbase + ci] = v;
                 }
               }
               const unsigned zi = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
@@ -276,12 +337,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           if (ncap > 0) {
 #pragma unroll
             for (int k = 0; k < FAST_EPT; ++k) {
-              const int st = (int)(bo[k] & 0xfffu);
               if (lane + 32 * k < niter && !(shared_mask & (1u << k))) {
-                for (int ci = 0; ci < ncap; ++ci) {
-                  const int cp = pass == 0 ? a.cap_pos[ci] : (ci == 0 ? fmA : fmB);
-                  if (st == cp) cap[cbase + ci] = (double)x[k];
-                }
+                const unsigned m = WANT[bo[k] & 0xfffu];
+                if (m) for (int ci = 0; ci < 6; ++ci) if (m & (1u << ci)) cap[cbase + ci] = (double)x[k];
               }
             }
           }
@@ -322,8 +380,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       }
 
       for (int r = 0; r < nred; ++r) {
-      const FastRed rd = pass == 1 ? a.p1_red : (r == 0 ? a.p0_red[0] : (r == 1 ? a.p0_red[1] : a.p0_red[2]));
-      const int slot = pass == 0 ? r : 3;
+      const FastRed rd = pass == 1 ? a.p1_red : (r == 0 ? a.p0_red[0] : (r == 1 ? a.p0_red[1] : (r == 2 ? a.p0_red[2] : (r == 3 ? a.p0_red[3] : a.p0_red[4]))));
+      const int slot = pass == 0 ? r : 5;
       // ---- the series this reduction runs on -----------------------------------------------------
       if (rd.src == FS_X) {
 #pragma unroll
@@ -333,17 +391,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
 #pragma unroll
         for (int k = 0; k < FAST_EPT; ++k) z[k] = ((double)x[k] <= tv) ? (T)1 : (T)0;
       } else if (rd.src == FS_SQDEV) {
-        double sx = 0.0;
-#pragma unroll
-        for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) sx += (double)x[k];
-        sx = warp_sum(sx);
-        __syncthreads();
-        if (lane == 0) wred[w] = sx;
-        __syncthreads();
-        double tot = 0.0;
-#pragma unroll
-        for (int i = 0; i < FAST_NCH; ++i) tot += wred[i];
-        const T mean_all = (T)(tot / (double)n);
+        const T mean_all = (T)side[0];
 #pragma unroll
         for (int k = 0; k < FAST_EPT; ++k) { const T d = x[k] - mean_all; z[k] = d * d; }
       }
@@ -376,7 +424,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       g8.niter = niter; g8.nch = FAST_NCH;
       T W, var_plus;
       within_between<T>(cmean, cvar, g8, W, var_plus);
-      if (tid == 0) { res[4 + slot] = (double)sqrt(var_plus / W); res[slot] = (double)Traits<T>::nan(); }
+      if (tid == 0) { res[6 + slot] = (double)sqrt(var_plus / W); res[slot] = (double)Traits<T>::nan(); }
       if (!do_ess) continue;
 
       // ---- direct autocovariance, lazily, Geyer truncation (ess_rhat.jl:553-594) -----------------
@@ -440,48 +488,27 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       if (redo) break;
     }
 
-    // mcse side statistics over all draws x chains (x still holds the raw values: no fold in these programs)
-    T mcse_a = (T)0, mcse_b = (T)0;
-    if (a.mcse_mode && !redo) {
-      auto block_total = [&](double v) -> double {
-        v = warp_sum(v);
-        __syncthreads();
-        if (lane == 0) wred[w] = v;
-        __syncthreads();
-        double t = 0.0;
-#pragma unroll
-        for (int i = 0; i < FAST_NCH; ++i) t += wred[i];
-        return t;
-      };
-      double sx = 0.0;
-#pragma unroll
-      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) sx += (double)x[k];
-      const T mean_all = (T)(block_total(sx) / (double)n);
-      double s2 = 0.0, s4 = 0.0;
-#pragma unroll
-      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) {
-        const T d = x[k] - mean_all;
-        const T pz = d * d;
-        s2 += (double)pz;
-        s4 = fma((double)pz, (double)pz, s4);
-      }
-      const double t2 = block_total(s2);
-      if (a.mcse_mode == 1) mcse_a = sqrt((T)(t2 / (double)(n - 1)));          // std(x; corrected)
-      else { mcse_a = (T)(t2 / (double)n); mcse_b = (T)(block_total(s4) / (double)n); }   // mean(proxy), mean(proxy^2)
-    }
     if (redo) {
       if (tid == 0) { const int idx = atomicAdd(a.redo_count, 1); a.redo_list[idx] = (int)param; }
     } else if (tid == 0) {
+      if (a.sum_mode) {
+        // the reference calls each column stands for: src/mcse.jl:45-69, src/ess_rhat.jl:298-311, 410-420, 604-624
+        if (a.col[2]) a.col[2][param] = (T)side[1] / sqrt((T)res[a.s_mean]);
+        if (a.col[3]) { const T m2 = (T)side[2], m4 = (T)side[3]; a.col[3][param] = sqrt((m4 / m2 - m2) / (T)res[a.s_std]) / (T)2; }
+        if (a.col[4]) a.col[4][param] = (T)res[a.s_bulk];
+        if (a.col[5]) a.col[5][param] = jl_min<T>((T)res[a.s_tlo], (T)res[a.s_thi]);
+        if (a.col[6]) a.col[6][param] = jl_max<T>((T)res[6 + 5], (T)res[6 + a.s_bulk]);
+      }
       if (a.ess_out) {
-        T e = (T)res[a.ess_mode == 4 ? 3 : 0];
+        T e = (T)res[a.ess_mode == 4 ? 5 : 0];
         if (a.ess_mode == 2) e = jl_min<T>(e, (T)res[1]);
-        if (a.mcse_mode == 1) e = mcse_a / sqrt(e);
-        else if (a.mcse_mode == 2) e = sqrt((mcse_b / mcse_a - mcse_a) / e) / (T)2;
+        if (a.mcse_mode == 1) e = (T)side[1] / sqrt(e);
+        else if (a.mcse_mode == 2) { const T m2 = (T)side[2], m4 = (T)side[3]; e = sqrt((m4 / m2 - m2) / e) / (T)2; }
         a.ess_out[param] = e;
       }
       if (a.rhat_out) {
-        T rh = (T)res[4 + (a.rhat_mode == 2 ? 3 : 0)];
-        if (a.rhat_mode == 3) rh = jl_max<T>((T)res[4 + 3], rh);
+        T rh = (T)res[6 + (a.rhat_mode == 2 ? 5 : 0)];
+        if (a.rhat_mode == 3) rh = jl_max<T>((T)res[6 + 5], rh);
         a.rhat_out[param] = rh;
       }
     }

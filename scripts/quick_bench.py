@@ -36,3 +36,5 @@ timeit("ess median", lambda: m.ess(x, kind="median"))
 timeit("mcse mean", lambda: m.mcse(x, kind="mean"))
 timeit("mcse median", lambda: m.mcse(x, kind="median"))
 print("launches", ctx.stat("kernel_launches"))
+timeit("summary (7 columns, fused)", lambda: m.summary(x))
+timeit("summary bulk+tail+rhat", lambda: m.summary(x, fields=("ess_bulk", "ess_tail", "rhat")))
