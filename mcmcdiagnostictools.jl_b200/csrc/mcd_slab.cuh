@@ -835,16 +835,16 @@ __global__ void __launch_bounds__(THREADS) slab_kernel(const SlabArgs<T> a) {
         if (S != S) { ess = (double)Traits<T>::nan(); break; }
         if (!viewX) { build_view<T, THREADS>(X, n, K, CNT, B, a.bucket_limit, ms, a.flags); viewX = true; }
         if (ms->vs.nnan > 0) { ess = (double)Traits<T>::nan(); break; }
-        if (tid == 0 || tid == 32) {
+        {
           const double al = S * a.mcse_p + 1.0, be = S * (1.0 - a.mcse_p) + 1.0;
+          // ms->red[32..33] <- betainvcdf(al, be, Phi(+1)), betainvcdf(al, be, Phi(-1))   (mcse.jl:105-109)
+          betainc_inv_pair_block<THREADS>(al, be, 0.8413447460685429, 0.15865525393145705, ms->red, ms->red + 32);
           if (tid == 0) {
-            const double pu = betainc_inv(al, be, 0.8413447460685429);
-            long long u = (long long)ceil(pu * (double)n);
+            long long u = (long long)ceil(ms->red[32] * (double)n);
             u = u > n ? n : (u < 1 ? 1 : u);
             ms->thr[2] = (double)view_select<T>((int)u - 1, n, K, CNT, B, ms->vs);
-          } else {
-            const double pl = betainc_inv(al, be, 0.15865525393145705);
-            long long l = (long long)floor(pl * (double)n);
+          } else if (tid == 32) {
+            long long l = (long long)floor(ms->red[33] * (double)n);
             l = l < 1 ? 1 : (l > n ? n : l);
             ms->thr[3] = (double)view_select<T>((int)l - 1, n, K, CNT, B, ms->vs);
           }

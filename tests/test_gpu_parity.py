@@ -370,3 +370,17 @@ def test_empty_and_degenerate_shapes(mcd, o):
         S, R = mcd.ess_rhat(x1, split_chains=split)
         So, Ro = o.ess_rhat(x1, split_chains=split)
         assert close(S, So, RTOL64) and close(R, Ro, RTOL64)
+
+
+def test_mcse_quantile_over_a_range_of_ess(mcd, o):
+    """The block-cooperative betainvcdf (quadrature + Newton) against the oracle's scipy inverse over a
+    wide range of Beta parameters (ESS from a few to the cap; src/mcse.jl:96-118)."""
+    r = rng(77)
+    cols = []
+    for phi in (-0.6, 0.0, 0.3, 0.6, 0.9, 0.98, 0.995):
+        cols.append(o.ar1(phi, np.sqrt(1 - phi * phi), 400, 4, 12, rng=r))
+    x = np.concatenate(cols, axis=2)
+    for kind, okind in ((np.median, "median"), (mcd.Quantile(0.1), o.Quantile(0.1)), (mcd.Quantile(0.93), o.Quantile(0.93))):
+        got = mcd.mcse(x, kind=kind)
+        want = o.mcse(x, kind=okind)
+        assert close(got, want, RTOL64), (kind, np.max(np.abs(got / want - 1)))
