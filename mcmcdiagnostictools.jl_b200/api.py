@@ -24,6 +24,8 @@ import warnings
 from collections import namedtuple
 from fractions import Fraction
 
+import math
+
 import numpy as np
 
 from . import _lib as L
@@ -35,9 +37,12 @@ __all__ = [
     "Quantile", "ArgumentError", "DomainError", "DimensionMismatch",
     "Context", "get_context", "tiedrank", "rank_normalize", "fold_around_median",
     "generate_ar1", "ESSRhat", "summary", "SUMMARY_FIELDS",
+    "gewekediag", "heideldiag", "GewekeResult", "HeidelResult",
 ]
 
 ESSRhat = namedtuple("ESSRhat", ["ess", "rhat"])
+GewekeResult = namedtuple("GewekeResult", ["zscore", "pvalue"])
+HeidelResult = namedtuple("HeidelResult", ["burnin", "stationarity", "pvalue", "mean", "halfwidth", "test"])
 # columns of `summary`, in the bit order of MCD_SUM_* (include/mcmcdiag_b200.h)
 SUMMARY_FIELDS = ("mean", "std", "mcse_mean", "mcse_std", "ess_bulk", "ess_tail", "rhat")
 
@@ -566,3 +571,126 @@ def generate_ar1(phi, sigma, draws, chains, params, *, dtype="float64", seed=1, 
                                    C.c_void_p(buf.data_ptr()))
     ctx.check(rc)
     return buf.permute(2, 1, 0)
+
+
+# ---------------------------------------------------------------------------------------
+# in-package callers of the path: thin host wrappers over the device mcse
+# ---------------------------------------------------------------------------------------
+def _series(x):
+    """(draws,) or (draws, params) -> host float matrix (draws, P), the input itself viewed as
+    (draws, 1, P) for the device calls, and whether the input was a single vector."""
+    is_torch = type(x).__module__.split(".")[0] == "torch"
+    nd = x.ndim if hasattr(x, "ndim") else np.asarray(x).ndim
+    if nd not in (1, 2):
+        raise ArgumentError("expected a vector of draws or a (draws, parameters) matrix")
+    if is_torch:
+        x3 = x.reshape(x.shape[0], 1, -1)
+        host = x3[:, 0, :].detach().cpu().numpy()
+    else:
+        x = np.asarray(x)
+        x3 = x.reshape(x.shape[0], 1, -1)
+        host = x3[:, 0, :]
+    T = np.float32 if host.dtype == np.float32 else np.float64
+    return host.astype(T, copy=False), x3, nd == 1, T
+
+
+def _window_mean_mcse(x3, lo, hi, ctx, kwargs):
+    """mean and mcse(...; split_chains=1, kwargs...) of draws [lo, hi) of every series, on the device."""
+    w = x3[lo:hi]
+    if "kind" in kwargs:
+        se = mcse(w, split_chains=1, ctx=ctx, **kwargs)
+        mu = summary(w, fields=("mean",), split_chains=1, ctx=ctx)["mean"]
+    else:
+        r = summary(w, fields=("mean", "mcse_mean"), split_chains=1, ctx=ctx, **kwargs)
+        mu, se = r["mean"], r["mcse_mean"]
+    to_np = lambda v: v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+    return to_np(mu).reshape(-1), to_np(se).reshape(-1)
+
+
+def gewekediag(x, *, first=0.1, last=0.5, ctx=None, **kwargs):
+    """`gewekediag(x::AbstractVector; first=0.1, last=0.5, kwargs...)` (src/gewekediag.jl:19-35):
+    z-score and p-value comparing the means of the first and last windows, their standard errors
+    from `mcse(...; split_chains=1, kwargs...)` on the device.  Extension: a `(draws, params)`
+    matrix runs every column in the same two device calls and returns arrays."""
+    from scipy import special
+    if not 0 < first < 1:
+        raise ArgumentError("`first` is not in (0, 1)")
+    if not 0 < last < 1:
+        raise ArgumentError("`last` is not in (0, 1)")
+    if not first + last <= 1:
+        raise ArgumentError("`first` and `last` proportions overlap")
+    host, x3, vector, T = _series(x)
+    n = host.shape[0]
+    hi1 = int(np.round(first * n))                      # x[1:round(Int, first * n)]
+    lo2 = int(np.round(n - last * n + 1)) - 1           # x[round(Int, n - last * n + 1):n]
+    m1, s1 = _window_mean_mcse(x3, 0, hi1, ctx, kwargs)
+    m2, s2 = _window_mean_mcse(x3, lo2, n, ctx, kwargs)
+    with np.errstate(all="ignore"):
+        z = ((m1.astype(T) - m2.astype(T)) / np.hypot(s1.astype(T), s2.astype(T))).astype(T)
+        p = special.erfc(np.abs(z.astype(np.float64)) / np.sqrt(2.0)).astype(T)
+    if vector:
+        return GewekeResult(T(z[0]), T(p[0]))
+    return GewekeResult(z, p)
+
+
+def _pcramer(q):
+    """Csorgo & Faraway (1996) series for the Cramer-von Mises distribution (src/heideldiag.jl:60-71)."""
+    from scipy import special
+    q = np.asarray(q, dtype=np.float64)
+    p = np.zeros_like(q)
+    with np.errstate(all="ignore"):
+        for k in range(4):
+            c1 = 4.0 * k + 1.0
+            c2 = c1 * c1 / (16.0 * q)
+            p += special.gamma(k + 0.5) / math.factorial(k) * math.sqrt(c1) * np.exp(-c2) * special.kv(0.25, c2)
+        return p / (math.pi ** 1.5 * np.sqrt(q))
+
+
+def heideldiag(x, *, alpha=Fraction(1, 20), eps=0.1, start=1, ctx=None, **kwargs):
+    """`heideldiag(x::AbstractVector; alpha=1//20, eps=0.1, start=1, kwargs...)` (src/heideldiag.jl:16-54):
+    Heidelberger-Welch stationarity (Cramer-von Mises on the Brownian-bridge statistic, discarding
+    10 % of the draws at a time) and half-width tests; both spectral-density-at-zero estimates are
+    `mcse(...; split_chains=1, kwargs...)` on the device.  Extension: a `(draws, params)` matrix is
+    processed column-wise with the device calls batched over the columns that share a burn-in."""
+    from scipy import special
+    host, x3, vector, T = _series(x)
+    n, P = host.shape
+    delta = int(0.10 * n)
+    lo = int(n / 2) - 1                                   # y = x[trunc(Int, n / 2):end]
+    _, s = _window_mean_mcse(x3, lo, n, ctx, kwargs)
+    S0 = T(n - lo) * s.astype(T) * s.astype(T)
+    burn = np.ones(P, dtype=np.int64)                     # i of the reference loop, per series
+    y_start = np.full(P, max(int(n / 2), 1), dtype=np.int64)   # 1-based start of the last y a series tested
+    pvalue = np.ones(P, dtype=T)
+    converged = np.zeros(P, dtype=bool)
+    ybar = np.full(P, np.nan, dtype=T)
+    active = np.ones(P, dtype=bool)
+    i = 1
+    while i < n / 2 and active.any():
+        idx = np.flatnonzero(active)
+        y = host[i - 1:, idx]
+        m = y.shape[0]
+        yb = y.mean(axis=0, dtype=T).astype(T)
+        with np.errstate(all="ignore"):
+            B = np.cumsum(y, axis=0, dtype=T) - yb[None, :] * np.arange(1, m + 1, dtype=T)[:, None]
+            I = ((B * B) / (T(m) * S0[idx])[None, :]).sum(axis=0, dtype=T) / T(m)
+            pv = (T(1) - _pcramer(I).astype(T)).astype(T)
+        ok = pv > float(alpha)
+        burn[idx], y_start[idx], pvalue[idx], ybar[idx], converged[idx] = i, i, pv, yb, ok
+        active[idx[ok]] = False
+        if delta == 0:                                    # n < 10: the reference loop would never advance
+            break
+        i += delta
+        burn[active] = i                                  # the reference adds delta before its loop test fails
+    halfwidth = np.empty(P, dtype=T)
+    for ys in np.unique(y_start):                         # s = mcse(y) on the last y each series tested
+        cols = np.flatnonzero(y_start == ys)
+        _, se = _window_mean_mcse(x3[:, :, cols], int(ys) - 1, n, ctx, kwargs)
+        halfwidth[cols] = (T(math.sqrt(2.0)) * T(special.erfcinv(float(T(float(alpha))))) * se.astype(T)).astype(T)
+    with np.errstate(all="ignore"):
+        passed = halfwidth / np.abs(ybar) <= eps
+    out = HeidelResult(burn + start - 2, converged, pvalue, ybar, halfwidth, passed)
+    if vector:
+        return HeidelResult(int(out.burnin[0]), bool(out.stationarity[0]), T(out.pvalue[0]), T(out.mean[0]),
+                            T(out.halfwidth[0]), bool(out.test[0]))
+    return out

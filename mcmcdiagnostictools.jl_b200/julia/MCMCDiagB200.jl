@@ -15,9 +15,11 @@ module MCMCDiagB200
 
 using Statistics: Statistics
 using StatsBase: StatsBase
+using SpecialFunctions: SpecialFunctions
 
 export ess, ess_rhat, rhat, rhat_nested, mcse
 export summary_columns
+export gewekediag, heideldiag
 export AutocovMethod, FFTAutocovMethod, BDAAutocovMethod
 export ESSMethod, FFTESSMethod, BDAESSMethod
 
@@ -283,6 +285,58 @@ function rhat_nested(samples::AbstractArray{<:Union{Missing,Real}}, superchain_i
         _check(rc)
     end
     return _unpack(samples, T, out, keep)
+end
+
+
+# ---- in-package callers of the path (src/gewekediag.jl:19-35, src/heideldiag.jl:16-71): unchanged host logic,
+# their two `mcse(...; split_chains=1)` calls land on the device through `mcse` above --------------------------
+function gewekediag(x::AbstractVector{<:Real}; first::Real=0.1, last::Real=0.5, kwargs...)
+    0 < first < 1 || throw(ArgumentError("`first` is not in (0, 1)"))
+    0 < last < 1 || throw(ArgumentError("`last` is not in (0, 1)"))
+    first + last <= 1 || throw(ArgumentError("`first` and `last` proportions overlap"))
+    n = length(x)
+    x1 = x[1:round(Int, first * n)]
+    x2 = x[round(Int, n - last * n + 1):n]
+    s = hypot(Base.first(mcse(reshape(x1, :, 1, 1); split_chains=1, kwargs...)),
+              Base.first(mcse(reshape(x2, :, 1, 1); split_chains=1, kwargs...)))
+    z = (Statistics.mean(x1) - Statistics.mean(x2)) / s
+    return (zscore=z, pvalue=SpecialFunctions.erfc(abs(z) / sqrt(2)))
+end
+
+function heideldiag(x::AbstractVector{<:Real}; alpha::Real=1//20, eps::Real=0.1, start::Int=1, kwargs...)
+    n = length(x)
+    delta = trunc(Int, 0.10 * n)
+    y = x[trunc(Int, n / 2):end]
+    T = typeof(zero(eltype(x)) / 1)
+    s = Base.first(mcse(reshape(y, :, 1, 1); split_chains=1, kwargs...))
+    S0 = length(y) * s^2
+    i, pvalue, converged, ybar = 1, one(T), false, T(NaN)
+    while i < n / 2
+        y = x[i:end]
+        m = length(y)
+        ybar = Statistics.mean(y)
+        B = cumsum(y) - ybar * collect(1:m)
+        I = sum((B .* B) ./ (m * S0)) / m
+        pvalue = 1 - T(_pcramer(I))
+        converged = pvalue > alpha
+        converged && break
+        i += delta
+    end
+    s = Base.first(mcse(reshape(y, :, 1, 1); split_chains=1, kwargs...))
+    halfwidth = sqrt(2) * SpecialFunctions.erfcinv(T(alpha)) * s
+    return (burnin=i + start - 2, stationarity=converged, pvalue=pvalue, mean=ybar, halfwidth=halfwidth,
+            test=halfwidth / abs(ybar) <= eps)
+end
+
+# Csorgo & Faraway (1996) series for the Cramer-von Mises distribution
+function _pcramer(q::Real)
+    p = 0.0
+    for k in 0:3
+        c1 = 4.0 * k + 1.0
+        c2 = c1^2 / (16.0 * q)
+        p += SpecialFunctions.gamma(k + 0.5) / factorial(k) * sqrt(c1) * exp(-c2) * SpecialFunctions.besselk(0.25, c2)
+    end
+    return p / (pi^1.5 * sqrt(q))
 end
 
 end # module

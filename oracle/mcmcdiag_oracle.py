@@ -750,3 +750,76 @@ def ar1(phi, sigma, *shape, rng=None, dtype=np.float64):
     for t in range(1, shape[0]):
         x[t] = phi * x[t - 1] + x[t]
     return x
+
+
+# ----------------------------------------------------------------------------------------
+# callers of the path: gewekediag (src/gewekediag.jl:19-35), heideldiag (src/heideldiag.jl:16-71)
+# ----------------------------------------------------------------------------------------
+def _jl_round_int(v):
+    return int(np.round(v))          # Julia round(Int, x): ties to even, as numpy
+
+
+def pcramer(q):
+    """Csorgo & Faraway (1996) series for the Cramer-von Mises distribution (src/heideldiag.jl:60-71)."""
+    from scipy import special
+    q = float(q)
+    p = 0.0
+    for k in range(4):
+        c1 = 4.0 * k + 1.0
+        c2 = c1 * c1 / (16.0 * q)
+        p += special.gamma(k + 0.5) / math.factorial(k) * math.sqrt(c1) * math.exp(-c2) * special.kv(0.25, c2)
+    return p / (math.pi ** 1.5 * math.sqrt(q))
+
+
+def gewekediag(x, first=0.1, last=0.5, **kw):
+    """src/gewekediag.jl:19-35 on one vector."""
+    from scipy import special
+    if not 0 < first < 1:
+        raise ValueError("`first` is not in (0, 1)")
+    if not 0 < last < 1:
+        raise ValueError("`last` is not in (0, 1)")
+    if not first + last <= 1:
+        raise ValueError("`first` and `last` proportions overlap")
+    x = np.asarray(x)
+    T = _float_dtype(x)
+    n = x.shape[0]
+    x1 = x[: _jl_round_int(first * n)]
+    x2 = x[_jl_round_int(n - last * n + 1) - 1:]
+    s1 = mcse(x1.reshape(-1, 1, 1), kind="mean", split_chains=1, **kw)[0]
+    s2 = mcse(x2.reshape(-1, 1, 1), kind="mean", split_chains=1, **kw)[0]
+    s = T(np.hypot(s1, s2))
+    z = T((T(x1.astype(T).mean(dtype=T)) - T(x2.astype(T).mean(dtype=T))) / s)
+    pv = T(special.erfc(abs(float(z)) / math.sqrt(2.0)))
+    return {"zscore": z, "pvalue": pv}
+
+
+def heideldiag(x, alpha=Fraction(1, 20), eps=0.1, start=1, **kw):
+    """src/heideldiag.jl:16-54 on one vector."""
+    from scipy import special
+    x = np.asarray(x)
+    T = _float_dtype(x)
+    xf = x.astype(T)
+    n = x.shape[0]
+    delta = int(0.10 * n)
+    y = xf[int(n / 2) - 1:]
+    s = mcse(y.reshape(-1, 1, 1), kind="mean", split_chains=1, **kw)[0]
+    S0 = T(len(y)) * s * s
+    i, pvalue, converged, ybar = 1, T(1), False, T(np.nan)
+    while i < n / 2:
+        y = xf[i - 1:]
+        m = len(y)
+        ybar = T(y.mean(dtype=T))
+        B = np.cumsum(y, dtype=T) - ybar * np.arange(1, m + 1, dtype=T)
+        Bsq = (B * B) / (T(m) * S0)
+        I = T(Bsq.sum(dtype=T) / T(m))
+        with np.errstate(all="ignore"):
+            pvalue = T(1) - T(pcramer(I))
+        converged = bool(pvalue > float(alpha))
+        if converged or delta == 0:     # delta == 0 (n < 10) never advances in the reference
+            break
+        i += delta
+    s = mcse(y.reshape(-1, 1, 1), kind="mean", split_chains=1, **kw)[0]
+    halfwidth = T(math.sqrt(2.0)) * T(special.erfcinv(float(T(float(alpha))))) * s
+    passed = bool(halfwidth / abs(ybar) <= eps)
+    return {"burnin": i + start - 2, "stationarity": converged, "pvalue": pvalue, "mean": ybar,
+            "halfwidth": T(halfwidth), "test": passed}

@@ -337,3 +337,37 @@ def test_nested_iid_many_chains():
     ids = np.repeat(np.arange(8), 64)
     R = o.rhat_nested(x, ids)
     assert np.all(R > 1) and np.all(R < 1.01)
+
+
+# --- callers of the path -------------------------------------------------------
+def test_pcramer_known_critical_values():
+    """Cramer-von Mises limiting distribution: the classical critical values 0.34730 / 0.46136 / 0.74346
+    have probabilities 0.90 / 0.95 / 0.99 (Anderson & Darling 1952), src/heideldiag.jl:60-71."""
+    from oracle import mcmcdiag_oracle as o
+    for q, p in ((0.34730, 0.90), (0.46136, 0.95), (0.74346, 0.99)):
+        assert abs(o.pcramer(q) - p) < 2e-5
+
+
+def test_gewekediag_heideldiag_oracle_behaviour():
+    """test/gewekediag.jl:10-18 (exceptions), result fields and types (test/gewekediag.jl:2-7,
+    test/heideldiag.jl:2-7), and the qualitative contract: a stationary series passes, a series with
+    a strong transient fails both diagnostics."""
+    from oracle import mcmcdiag_oracle as o
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(100)
+    for v in (-0.3, 0, 1, 1.2):
+        with pytest.raises(ValueError):
+            o.gewekediag(x, first=v)
+        with pytest.raises(ValueError):
+            o.gewekediag(x, last=v)
+    with pytest.raises(ValueError):
+        o.gewekediag(x, first=0.6, last=0.5)
+    for T in (np.float32, np.float64):
+        g = o.gewekediag(x.astype(T))
+        assert set(g) == {"zscore", "pvalue"} and g["zscore"].dtype == T and g["pvalue"].dtype == T
+        h = o.heideldiag(x.astype(T))
+        assert set(h) == {"burnin", "stationarity", "pvalue", "mean", "halfwidth", "test"}
+    y = o.ar1(0.5, 0.8, 2000, 1, 1, rng=rng)[:, 0, 0]
+    assert o.gewekediag(y)["pvalue"] > 0.01 and o.heideldiag(y)["stationarity"]
+    bad = y + np.linspace(3, 0, 2000) ** 2
+    assert o.gewekediag(bad)["pvalue"] < 1e-6 and not o.heideldiag(bad)["stationarity"]
