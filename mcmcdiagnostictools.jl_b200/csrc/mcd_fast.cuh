@@ -207,6 +207,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
       }
       if (need_rank) {
         __syncthreads();  // previous users of the big region (ZC / K / CNT) are done
+        // clear the packed counters now: the barrier of the min / max exchange (pass 0) covers it
+        for (int i = tid; i < FAST_WORDS / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(FC)[i] = make_uint4(0, 0, 0, 0);
+        if (pass == 1) __syncthreads();
         if (pass == 0) {
           T lmin = (T)CUDART_INF, lmax = -(T)CUDART_INF;
           int bad = 0;
@@ -249,8 +252,6 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
           if (pass == 0 && tid == 0) { thr[0] = (double)vmin; thr[1] = (double)vmin; }
         } else {
           // ---- count: 4-bit packed populations, one atomic per element --------------------------
-          for (int i = tid; i < FAST_WORDS / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(FC)[i] = make_uint4(0, 0, 0, 0);
-          __syncthreads();
           unsigned bo[FAST_EPT];   // fine bucket | arrival offset << 16 ; later: packed rank info
           unsigned maxoff = 0, shared_mask = 0;
 #pragma unroll
@@ -295,8 +296,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
             }
             if (lane == 0) iflag[w] = (int)carry;
             __syncthreads();
-            if (tid < FAST_NCH) { int o = 0; for (int i = 0; i < tid; ++i) o += iflag[i]; woffx[tid] = o; }
-            __syncthreads();
+          }
+          // lane i < 8 holds the number of values in the ranges of warps 0 .. i-1
+          unsigned woff;
+          {
+            const unsigned tot = lane < FAST_NCH ? (unsigned)iflag[lane] : 0u;
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < FAST_NCH; o <<= 1) {
+              const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            woff = incl - tot;
           }
           // ---- position: start of the fine bucket, population, own slot; shared buckets scatter ----
 #pragma unroll
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
             const unsigned fb = bo[k] & 0xffffu, off = bo[k] >> 16;
             const unsigned word = fb >> 3, sh = (fb & 7u) * 4u;
             const unsigned fw = FC[word];
-            const unsigned st = (unsigned)WP[word] + (unsigned)woffx[word >> 10] + nibsum(fw & ((1u << sh) - 1u));
+            const unsigned st = (unsigned)WP[word] + __shfl_sync(0xffffffffu, woff, (int)(word >> 10)) + nibsum(fw & ((1u << sh) - 1u));
             const unsigned c = valid ? ((fw >> sh) & 15u) : 0u;
             if (c >= 2u) {
               Khi[st + off] = key_hi(x[k]);

@@ -153,6 +153,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       const bool first_is_rankz = (pass == 0 ? (nred > 0 && a.p0_red[0].src == FS_RANKZ) : a.p1_red.src == FS_RANKZ);
       if (need_rank) {
         __syncthreads();  // previous users of the big region (ZC / K / CNT) are done
+        // clear the packed counters now: the barrier of the min / max exchange (pass 0) covers it
+        for (int i = tid; i < FAST_WORDS / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(FC)[i] = make_uint4(0, 0, 0, 0);
+        if (pass == 1) __syncthreads();
         if (pass == 0) {
           T lmin = (T)CUDART_INF, lmax = -(T)CUDART_INF;
           int bad = 0;
@@ -195,8 +198,6 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           if (tid < 8) cap[tid] = (double)vmin;   // every order statistic equals the common value
         } else {
           // ---- count: 4-bit packed populations, one atomic per element --------------------------
-          for (int i = tid; i < FAST_WORDS / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(FC)[i] = make_uint4(0, 0, 0, 0);
-          __syncthreads();
           unsigned bo[FAST_EPT];   // fine bucket | arrival offset << 16 ; later: packed rank info
           unsigned maxoff = 0, shared_mask = 0;
 #pragma unroll
@@ -241,8 +242,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
             }
             if (lane == 0) iflag[w] = (int)carry;
             __syncthreads();
-            if (tid < FAST_NCH) { int o = 0; for (int i = 0; i < tid; ++i) o += iflag[i]; woffx[tid] = o; }
-            __syncthreads();
+          }
+          // lane i < 8 holds the number of values in the ranges of warps 0 .. i-1
+          unsigned woff;
+          {
+            const unsigned tot = lane < FAST_NCH ? (unsigned)iflag[lane] : 0u;
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < FAST_NCH; o <<= 1) {
+              const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            woff = incl - tot;
           }
           // ---- position: start of the fine bucket, population, own slot; shared buckets scatter ----
 #pragma unroll
@@ -251,7 +262,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
             const unsigned fb = bo[k] & 0xffffu, off = bo[k] >> 16;
             const unsigned word = fb >> 3, sh = (fb & 7u) * 4u;
             const unsigned fw = FC[word];
-            const unsigned st = (unsigned)WP[word] + (unsigned)woffx[word >> 10] + nibsum(fw & ((1u << sh) - 1u));
+            const unsigned st = (unsigned)WP[word] + __shfl_sync(0xffffffffu, woff, (int)(word >> 10)) + nibsum(fw & ((1u << sh) - 1u));
             const unsigned c = valid ? ((fw >> sh) & 15u) : 0u;
             if (c >= 2u) {
               Khi[st + off] = key_hi(x[k]);
