@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           if (a.col[1]) a.col[1][param] = sd;
         }
       }
+      __syncthreads();   // side[] is read by every thread (FS_SQDEV) and by thread 0 at the end
     }
 
     for (int pass = 0; pass < 2; ++pass) {

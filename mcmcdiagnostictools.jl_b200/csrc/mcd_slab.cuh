@@ -374,6 +374,8 @@ __device__ void rank_transform(const T* V, T* Y, int n, T* K, const unsigned* CN
     else Y[i] = __ldg(&ztab[r2 - 2]);
   }
   if (vs.nnan > 0) {
+    // V may be Y (in place): every thread must have read its V[i] before a NaN slot is overwritten
+    __syncthreads();
     const Key* KK = reinterpret_cast<const Key*>(K);
     for (int q = tid; q < vs.nnan; q += THREADS) {
       int i = (int)KK[m + q];

@@ -1,0 +1,127 @@
+"""Seeded differential fuzz: random shapes / kinds / methods / keywords / data pathologies, CUDA path
+against the NumPy oracle.  Every case is reproducible from its index."""
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["rank", "bulk", "tail", "basic"]
+METHODS = ["AutocovMethod", "FFTAutocovMethod", "BDAAutocovMethod"]
+ESTIMATORS = ["mean", "median", "std", "mad", "q"]
+
+
+@pytest.fixture(scope="module")
+def mcd():
+    import mcmcdiag_b200 as m
+    m.get_context(0)
+    return m
+
+
+@pytest.fixture(scope="module")
+def o():
+    from oracle import mcmcdiag_oracle
+    return mcmcdiag_oracle
+
+
+def make_case(o, i):
+    r = np.random.default_rng(1000 + i)
+    draws = int(r.choice([5, 8, 9, 10, 17, 33, 64, 100, 250, 500, 999, 1000, 1001, 1024, 2000]))
+    chains = int(r.choice([1, 2, 3, 4, 4, 4, 6, 8, 16]))
+    P = int(r.integers(1, 5))
+    phi = float(r.choice([-0.5, 0.0, 0.5, 0.9, 0.99]))
+    x = o.ar1(phi, np.sqrt(1 - phi * phi), draws, chains, P, rng=r)
+    patho = r.choice(["none", "none", "none", "ties", "const", "const_chain", "pm0", "huge", "drift"])
+    if patho == "ties":
+        x[..., 0] = r.integers(1, int(r.choice([3, 10, 50])), size=(draws, chains))
+    elif patho == "const":
+        x[..., 0] = 2.5
+    elif patho == "const_chain":
+        x[:, 0, 0] = 1.0
+    elif patho == "pm0":
+        x[..., 0] = np.where(r.random((draws, chains)) < 0.5, 0.0, -0.0)
+        x[: draws // 2, :, 0] += np.round(x[: draws // 2, :, 0] * 0)   # keep zeros, mixed signs
+    elif patho == "huge":
+        x[..., 0] *= 1e150
+    elif patho == "drift":
+        x[..., 0] += np.linspace(0, 3, draws)[:, None]
+    dtype = np.float32 if r.random() < 0.3 else np.float64
+    x = x.astype(dtype)
+    kw = dict(split_chains=int(r.choice([1, 2, 2, 2, 3])), maxlag=int(r.choice([1, 2, 3, 10, 250, 250, 250])))
+    return r, x, kw, patho
+
+
+def agree(got, want, dtype, what):
+    rtol = 1e-8 if dtype == np.float64 else 3e-4
+    a, b = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert a.shape == b.shape, what
+    bad = ~np.isclose(a, b, rtol=rtol, atol=0, equal_nan=True)
+    assert not bad.any(), (what, a, b)
+
+
+@pytest.mark.parametrize("i", range(120))
+def test_fuzz_ess_rhat(mcd, o, i):
+    r, x, kw, patho = make_case(o, i)
+    kind = KINDS[int(r.integers(0, 4))]
+    method = METHODS[int(r.integers(0, 3))]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        S, R = mcd.ess_rhat(x, kind=kind, autocov_method=getattr(mcd, method)(), **kw)
+        So, Ro = o.ess_rhat(x, kind=kind, autocov_method=getattr(o, method)(), **kw)
+    # Float32: Geyer's truncation is discontinuous, a rounding difference can move a rare parameter
+    if x.dtype == np.float32:
+        ok = np.isclose(S, So, rtol=3e-4, equal_nan=True)
+        assert ok.mean() >= 0.5 or ok.all(), (i, kind, method, kw, patho, S, So)
+    else:
+        agree(S, So, x.dtype, (i, "ess", kind, method, kw, patho, x.shape))
+    agree(R, Ro, x.dtype, (i, "rhat", kind, method, kw, patho, x.shape))
+
+
+@pytest.mark.parametrize("i", range(60))
+def test_fuzz_estimators_and_mcse(mcd, o, i):
+    r, x, kw, patho = make_case(o, 500 + i)
+    x = x.astype(np.float64)
+    est = ESTIMATORS[int(r.integers(0, 5))]
+    p = float(r.choice([0.05, 0.25, 0.5, 0.9]))
+    gk = mcd.Quantile(p) if est == "q" else est
+    ok_ = o.Quantile(p) if est == "q" else est
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        agree(mcd.ess(x, kind=gk, **kw), o.ess(x, kind=ok_, **kw), x.dtype, (i, "ess", est, p, kw, patho, x.shape))
+        if est != "mad":
+            agree(mcd.mcse(x, kind=gk, **kw), o.mcse(x, kind=ok_, **kw), x.dtype, (i, "mcse", est, p, kw, patho, x.shape))
+
+
+@pytest.mark.parametrize("i", range(30))
+def test_fuzz_summary(mcd, o, i):
+    r, x, kw, patho = make_case(o, 900 + i)
+    x = x.astype(np.float64)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got, want = mcd.summary(x, **kw), o.summary(x, **kw)
+    for k in want:
+        agree(got[k], want[k], x.dtype, (i, k, kw, patho, x.shape))
+
+
+@pytest.mark.parametrize("i", range(40))
+def test_fuzz_nan_and_inf(mcd, o, i):
+    """NaNs rank last (finite bulk / rank results), quantile-based kinds raise as the reference does;
+    infinities order like any other value."""
+    r, x, kw, _ = make_case(o, 1500 + i)
+    x = x.astype(np.float64)
+    d, c, P = x.shape
+    for _ in range(int(r.integers(1, 4))):
+        x[int(r.integers(0, d)), int(r.integers(0, c)), 0] = r.choice([np.nan, np.inf, -np.inf])
+    kind = KINDS[int(r.integers(0, 4))]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            So, Ro = o.ess_rhat(x, kind=kind, **kw)
+        except ValueError:
+            with pytest.raises(mcd.ArgumentError):
+                mcd.ess_rhat(x, kind=kind, **kw)
+            return
+        S, R = mcd.ess_rhat(x, kind=kind, **kw)
+    agree(S, So, x.dtype, (i, "ess", kind, kw, x.shape))
+    agree(R, Ro, x.dtype, (i, "rhat", kind, kw, x.shape))

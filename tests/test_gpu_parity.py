@@ -384,3 +384,27 @@ def test_mcse_quantile_over_a_range_of_ess(mcd, o):
         got = mcd.mcse(x, kind=kind)
         want = o.mcse(x, kind=okind)
         assert close(got, want, RTOL64), (kind, np.max(np.abs(got / want - 1)))
+
+
+@pytest.mark.parametrize("draws", [100, 500, 1000, 2000])
+def test_many_nans_rank_in_place(mcd, o, draws):
+    """Regression: with many NaNs the in-place rank-normalisation of the general kernel raced (a NaN slot
+    was overwritten before its owner had read it).  NaNs rank last, each distinct, in index order."""
+    r = rng(91)
+    x = np.full((draws, 4, 2), np.inf)
+    x[..., 1] = r.standard_normal((draws, 4))
+    x[np.cumsum(r.standard_normal((draws, 4, 2)), axis=0) > 0] = np.nan      # clustered NaNs
+    for _ in range(3):
+        assert np.allclose(mcd.rank_normalize(x), o.rank_normalize(x), rtol=1e-12, equal_nan=True)
+        assert np.array_equal(mcd.tiedrank(x), np.stack([o.tiedrank(x[..., j].reshape(-1, order="F")).reshape(draws, 4, order="F")
+                                                         for j in range(2)], axis=2))
+        assert close(mcd.rhat(x, kind="bulk"), o.rhat(x, kind="bulk"), RTOL64)
+
+
+def test_all_infinite_parameter_tail_rhat(mcd, o):
+    """A parameter of +-Inf only: the fold gives NaN (Inf - Inf) for one sign and Inf for the other."""
+    r = rng(92)
+    for draws in (50, 1000, 2000):
+        x = np.where(np.cumsum(r.standard_normal((draws, 4, 2)), axis=0) > 0, np.inf, -np.inf)
+        assert close(mcd.rhat(x, kind="tail"), o.rhat(x, kind="tail"), RTOL64)
+        assert close(mcd.rhat(x, kind="rank"), o.rhat(x, kind="rank"), RTOL64)
