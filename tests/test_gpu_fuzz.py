@@ -125,3 +125,57 @@ def test_fuzz_nan_and_inf(mcd, o, i):
         S, R = mcd.ess_rhat(x, kind=kind, **kw)
     agree(S, So, x.dtype, (i, "ess", kind, kw, x.shape))
     agree(R, Ro, x.dtype, (i, "rhat", kind, kw, x.shape))
+
+
+@pytest.mark.parametrize("i", range(40))
+def test_fuzz_rhat_nested(mcd, o, i):
+    r = np.random.default_rng(3000 + i)
+    nsuper = int(r.choice([2, 3, 4, 8]))
+    per = int(r.choice([1, 2, 4]))
+    chains = nsuper * per
+    draws = int(r.choice([6, 10, 50, 100, 333, 1000]))
+    P = int(r.integers(1, 4))
+    x = o.ar1(0.5, 0.8, draws, chains, P, rng=r)
+    if r.random() < 0.3:
+        x[..., 0] = r.integers(0, 6, size=(draws, chains))
+    ids = np.repeat(np.arange(nsuper), per)
+    r.shuffle(ids)
+    kind = KINDS[int(r.integers(0, 4))]
+    split = int(r.choice([1, 2, 3]))
+    got = mcd.rhat_nested(x, list(ids), kind=kind, split_chains=split)
+    want = o.rhat_nested(x, list(ids), kind=kind, split_chains=split)
+    agree(got, want, x.dtype, (i, kind, split, x.shape, ids))
+
+
+@pytest.mark.parametrize("i", range(40))
+def test_fuzz_paths_agree(mcd, i):
+    """The same call on the three kernel families (register-resident, shared-memory, global-memory)
+    gives the same numbers: no oracle involved, so larger parameter counts."""
+    from oracle import mcmcdiag_oracle as o
+    r = np.random.default_rng(4000 + i)
+    draws = int(r.choice([64, 500, 1000, 1000, 1000, 1500]))
+    chains = int(r.choice([2, 4, 4, 4, 8]))
+    P = int(r.integers(20, 60))
+    phi = float(r.choice([0.0, 0.5, 0.95]))
+    x = o.ar1(phi, np.sqrt(1 - phi * phi), draws, chains, P, rng=r)
+    x[..., 0] = np.round(x[..., 0], 1)
+    x[3, 1, 1] = np.nan
+    call = int(r.integers(0, 5))
+    fns = [lambda: np.stack(mcd.ess_rhat(x, kind="rank")), lambda: np.stack(mcd.ess_rhat(x[..., 2:], kind="tail")),
+           lambda: mcd.ess(x[..., 2:], kind="median"), lambda: mcd.mcse(x[..., 2:], kind="std"),
+           lambda: np.stack(list(mcd.summary(x[..., 2:]).values()))]
+    ctx = mcd.get_context(0)
+    outs = []
+    try:
+        for fp in (0, 1, 2):
+            ctx.set_option("force_path", fp)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                try:
+                    outs.append(np.asarray(fns[call]()))
+                except NotImplementedError:      # the forced family does not take this shape
+                    assert fp == 1 and draws * chains > 8000
+    finally:
+        ctx.set_option("force_path", 0)
+    for other in outs[1:]:
+        assert np.allclose(outs[0], other, rtol=1e-8, atol=0, equal_nan=True), (i, call, x.shape)
