@@ -179,3 +179,28 @@ def test_fuzz_paths_agree(mcd, i):
         ctx.set_option("force_path", 0)
     for other in outs[1:]:
         assert np.allclose(outs[0], other, rtol=1e-8, atol=0, equal_nan=True), (i, call, x.shape)
+
+
+@pytest.mark.parametrize("i", range(16))
+def test_fuzz_large_slabs(mcd, o, i):
+    """Slabs that only the global-memory pipeline takes (segmented sort, four-step FFT, long chains)."""
+    r = np.random.default_rng(5000 + i)
+    draws = int(r.choice([3000, 7001, 20000, 40000, 70000]))
+    chains = int(r.choice([1, 2, 4, 6]))
+    P = int(r.integers(1, 4))
+    phi = float(r.choice([0.0, 0.7, 0.98]))
+    x = o.ar1(phi, np.sqrt(1 - phi * phi), draws, chains, P, rng=r)
+    if r.random() < 0.4:
+        x[..., 0] = np.round(x[..., 0], int(r.choice([0, 1, 2])))      # heavy ties
+    if r.random() < 0.3:
+        x[int(r.integers(0, draws)), 0, P - 1] = np.nan
+    kind = ["rank", "bulk", "basic"][int(r.integers(0, 3))]
+    method = METHODS[int(r.integers(0, 3))]
+    kw = dict(split_chains=int(r.choice([1, 2, 3])), maxlag=int(r.choice([10, 250, 1000])))
+    S, R = mcd.ess_rhat(x, kind=kind, autocov_method=getattr(mcd, method)(), **kw)
+    So, Ro = o.ess_rhat(x, kind=kind, autocov_method=getattr(o, method)(), **kw)
+    agree(S, So, x.dtype, (i, "ess", kind, method, kw, x.shape))
+    agree(R, Ro, x.dtype, (i, "rhat", kind, method, kw, x.shape))
+    if not np.isnan(x).any():
+        est = ["median", "std", "mean"][int(r.integers(0, 3))]
+        agree(mcd.mcse(x, kind=est, **kw), o.mcse(x, kind=est, **kw), x.dtype, (i, "mcse", est, kw, x.shape))
