@@ -92,7 +92,8 @@ int mcd_synchronize(mcd_ctx* ctx);
  * "h2d_chunk_bytes", "workspace_bytes", "sort_bucket_limit". */
 int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value);
 /* Counters.  Keys: "kernel_launches" (since creation), "last_path" (1 slab, 2 large, 3 fast),
- * "h2d_bytes", "d2h_bytes", "sm_count". */
+ * "h2d_bytes", "d2h_bytes", "sm_count", "smem_optin", "redo_count" (parameters the register-resident
+ * kernel handed to the general kernel in the last launch: NaN, infinite range, heavy ties, ...). */
 int64_t mcd_get_stat(const mcd_ctx* ctx, const char* key);
 
 /* ---- the hot path ---------------------------------------------------------------- */

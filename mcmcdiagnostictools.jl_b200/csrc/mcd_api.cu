@@ -428,6 +428,14 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
     a.p0_nred = 1; a.p0_red[0].src = FS_X; a.p0_red[0].want_ess = 1; a.ess_mode = 1; a.mcse_mode = 1; a.need_side = 1;
   } else if (pg.nsteps == 1 && pg.combine == CB_MCSE_STD && s0.transform == TR_STDPROXY && s0.reduce == RD_ESS_RHAT) {
     a.p0_nred = 1; a.p0_red[0].src = FS_SQDEV; a.p0_red[0].want_ess = 1; a.ess_mode = 1; a.mcse_mode = 2; a.need_side = 1;
+  } else if (pg.nsteps == 1 && pg.combine == CB_MCSE_QUANTILE && s0.reduce == RD_ESS_RHAT &&
+             (s0.transform == TR_IND_MEDIAN || s0.transform == TR_IND_QUANTILE)) {
+    // _mcse_quantile (src/mcse.jl:96-118): indicator ESS, then two order statistics around p n from the kept window
+    a.p0_rank = 1; a.p0_nred = 1; ind_red(0, 0); a.ess_mode = 1; a.mcse_mode = 3; a.mcse_p = pg.mcse_p;
+    if (s0.transform == TR_IND_MEDIAN) { a.ncap = 2; a.nthr = 1; a.thr[0].quantile = 0; a.thr[0].capA = 0; a.thr[0].capB = 1; }
+    else { a.ncap = 4; a.nthr = 1; quantile_plan(s0.p, s0.p_f32, 2, 0); }
+    const long long centre = std::llround(pg.mcse_p * (double)n);
+    a.win_lo = (int)std::min<long long>(std::max<long long>(centre - FASTGEN_WIN / 2, 0), std::max<long long>(n - FASTGEN_WIN, 0));
   } else if ((pg.combine == CB_TAIL && pg.nsteps == 3) || (pg.combine == CB_TAIL_ESS && pg.nsteps == 2)) {
     // _ess(Val(:tail)): min of the two quantile-indicator ESS (src/ess_rhat.jl:301-311) [+ tail R-hat]
     if (s0.transform != TR_IND_QUANTILE || pg.steps[1].transform != TR_IND_QUANTILE) return MCD_OK;
@@ -473,7 +481,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
     kern<<<grid, FAST_THREADS, smem, ctx->stream>>>(a);
   } else {
     const size_t smem = fast_smem_bytes<T>(pg.maxlag) + FASTGEN_EXTRA_SMEM + (size_t)ctx->fast_pad_smem;
-    auto kern = fastgen_kernel<T>;
+    auto kern = ga.mcse_mode == 3 ? fastgen_kernel<T, true> : fastgen_kernel<T, false>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(ga);
   }
@@ -556,7 +564,7 @@ static int run_fast_summary(mcd_ctx* ctx, const T* dx, long long params, const S
   a.redo_count = ctx->d_redo; a.redo_list = ctx->d_redo + 1;
   CU(cudaMemsetAsync(ctx->d_redo, 0, sizeof(int), ctx->stream));
   const size_t smem = fast_smem_bytes<T>(a.maxlag) + FASTGEN_EXTRA_SMEM + (size_t)ctx->fast_pad_smem;
-  auto kern = fastgen_kernel<T>;
+  auto kern = fastgen_kernel<T, false>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(a);
   ctx->launches++;
@@ -882,6 +890,14 @@ int64_t mcd_get_stat(const mcd_ctx* ctx, const char* key) {
   if (k == "last_path") return ctx->last_path;
   if (k == "h2d_bytes") return ctx->h2d_bytes;
   if (k == "d2h_bytes") return ctx->d2h_bytes;
+  if (k == "redo_count") {   // parameters the register-resident kernel handed to the general kernel in the last call (last chunk)
+    if (!ctx->d_redo) return 0;
+    int v = 0;
+    cudaSetDevice(ctx->device);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, ctx->d_redo, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
+  }
   if (k == "sm_count") return ctx->sm_count;
   if (k == "smem_optin") return ctx->smem_optin;
   return -1;

@@ -249,11 +249,12 @@ __device__ inline double beta_rel_gl8(double am1, double bm1, double x0, double 
 }
 template <int THREADS>
 __device__ void betainc_inv_pair_block(double a, double b, double p0, double p1, double* red, double* out) {
+  static_assert(THREADS >= 64 && THREADS % 32 == 0 && THREADS <= 1024, "two warps run the Newton steps");
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const bool ok = a >= 16.0 && b >= 16.0 && p0 > 0.0 && p0 < 1.0 && p1 > 0.0 && p1 < 1.0;   // uniform over the block
   if (!ok) {
     if (tid == 0) out[0] = betainc_inv(a, b, p0);
-    if (tid == 32 % THREADS) out[1] = betainc_inv(a, b, p1);
+    if (tid == 32) out[1] = betainc_inv(a, b, p1);
     __syncthreads();
     return;
   }
@@ -263,7 +264,10 @@ __device__ void betainc_inv_pair_block(double a, double b, double p0, double p1,
   const double L = fmax(0.0, x0 - 40.0 * sd), R = fmin(1.0, x0 + 40.0 * sd);
   const double h = (R - L) / (double)THREADS;
   const double xl = L + h * (double)tid, xr = tid == THREADS - 1 ? R : L + h * (double)(tid + 1);
-  const double mass = beta_rel_gl8(am1, bm1, x0, xl, xr);
+  // a panel whose density is < 1e-30 of the mode's at its nearer edge carries no mass that matters
+  // (the window is 80 sd wide: whole warps skip the quadrature)
+  const double edge = xr < x0 ? xr : (xl > x0 ? xl : x0);
+  const double mass = beta_rel_pdf(am1, bm1, x0, edge) < 1e-30 ? 0.0 : beta_rel_gl8(am1, bm1, x0, xl, xr);
   double incl = mass;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -272,27 +276,50 @@ __device__ void betainc_inv_pair_block(double a, double b, double p0, double p1,
   }
   __syncthreads();   // red is free
   if (lane == 31) red[w] = incl;
-  if (tid == 0) { out[0] = x0; out[1] = x0; }
   __syncthreads();
   double before = 0.0, total = 0.0;
 #pragma unroll
   for (int i = 0; i < THREADS / 32; ++i) { const double t = red[i]; if (i < w) before += t; total += t; }
   const double cr = (before + incl) / total, cl = (before + incl - mass) / total;
+  __syncthreads();   // every thread has read red[0 .. THREADS/32): reuse red[0..7] for the two brackets
+  if (tid == 0) { red[0] = red[4] = x0; red[1] = red[5] = x0; red[2] = red[6] = 0.0; red[3] = red[7] = 0.0; }
+  __syncthreads();
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const double p = q == 0 ? p0 : p1;
     const bool mine = (cl <= p && p < cr) || (tid == THREADS - 1 && p >= cr);
-    if (mine && cr > cl) {
-      double x = xl + (xr - xl) * (p - cl) / (cr - cl);
+    if (mine && cr > cl) { red[4 * q] = xl; red[4 * q + 1] = xr; red[4 * q + 2] = cl; red[4 * q + 3] = cr; }
+  }
+  __syncthreads();
+  if (w < 2) {
+    // warp q solves I(x) = p_q inside its bracketing panel: lanes 0..7 hold the Gauss-Legendre nodes of
+    // [edge, x], lane 8 the density at x; one density evaluation of latency per Newton step
+    const double p = w == 0 ? p0 : p1;
+    const double bl = red[4 * w], br = red[4 * w + 1], bcl = red[4 * w + 2], bcr = red[4 * w + 3];
+    double x = bl;
+    if (bcr > bcl) {
+      const double NODE[4] = {0.1834346424956498, 0.5255324099163290, 0.7966664774136267, 0.9602898564975363};
+      const double WGT[4] = {0.3626837833783620, 0.3137066458778873, 0.2223810344533745, 0.1012285362903763};
+      const double nd = lane < 8 ? ((lane & 1) ? NODE[(lane >> 1) & 3] : -NODE[(lane >> 1) & 3]) : 0.0;
+      const double wt = lane < 8 ? WGT[(lane >> 1) & 3] : 0.0;
+      x = bl + (br - bl) * (p - bcl) / (bcr - bcl);
       for (int it = 0; it < 8; ++it) {
-        const double I = cl + beta_rel_gl8(am1, bm1, x0, xl, x) / total;
-        const double dx = (I - p) / (beta_rel_pdf(am1, bm1, x0, x) / total);
+        const double xm = 0.5 * (bl + x), xh = 0.5 * (x - bl);
+        const double at = lane < 8 ? xm + xh * nd : x;
+        double v = lane <= 8 ? beta_rel_pdf(am1, bm1, x0, at) : 0.0;
+        const double fx = __shfl_sync(0xffffffffu, v, 8);
+        v *= wt;
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        const double integral = __shfl_sync(0xffffffffu, v, 0) * xh;
+        const double dx = (bcl + integral / total - p) / (fx / total);
         x -= dx;
-        x = x < xl ? xl : (x > xr ? xr : x);
+        x = x < bl ? bl : (x > br ? br : x);
         if (fabs(dx) <= 1e-16 * x) break;
       }
-      out[q] = x;
     }
+    if (lane == 0) out[w] = x;
   }
   __syncthreads();
 }

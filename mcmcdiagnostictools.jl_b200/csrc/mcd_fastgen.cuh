@@ -27,6 +27,9 @@ struct FastRed { int src, want_ess, thr; };
 // threshold from captured order statistics: median a/2 + b/2, or type-7 quantile a + g (b - a)
 struct FastThr { int quantile, capA, capB, f32; double g; };
 
+constexpr int FASTGEN_WIN = 1024;           // window of sorted positions kept for late order statistics (mcse quantile rule)
+static_assert(FAST_NCH * FAST_ROW * 8 + FASTGEN_WIN * 8 <= FAST_OFF_KHI, "WIN must fit behind ZC in the counter / prefix region");
+static_assert(FAST_NMAX * 4 + FAST_NMAX * 2 + FAST_NMAX <= FAST_WORDS * 4, "work list + RES + WANT must fit in the counter region");
 constexpr int FASTGEN_EXTRA_SMEM = 24 * 8;   // cap[8] + thrv[4] + res[12] + side[4] replace the lean kernel's thr[4]
 
 template <typename T> struct FastGenArgs {
@@ -45,7 +48,10 @@ template <typename T> struct FastGenArgs {
   FastRed p1_red;       // reduction on the folded data -> result slot 5 (FS_IND uses the median of the folded values)
   int ess_mode;         // 0 none, 1 slot 0, 2 min(slot 0, slot 1), 4 slot 5
   int rhat_mode;        // 0 none, 1 slot 0, 2 slot 5, 3 max(slot 5, slot 0)
-  int mcse_mode;        // 0 none, 1 mean: std(x)/sqrt(ess) (mcse.jl:45-51), 2 std: sqrt((m4/m2 - m2)/ess)/2 (mcse.jl:52-65)
+  int mcse_mode;        // 0 none, 1 mean: std(x)/sqrt(ess) (mcse.jl:45-51), 2 std: sqrt((m4/m2 - m2)/ess)/2 (mcse.jl:52-65),
+                        // 3 median / quantile: order-statistic rule (mcse.jl:96-118) on result slot 0
+  double mcse_p;        // mode 3: the quantile's probability
+  int win_lo;           // mode 3: first sorted position kept in WIN
   int need_side;        // mean / std / m2 / m4 over all draws and chains (mcse rules, FS_SQDEV, summary)
   // fused summary (mcd_summary): columns mean, std, mcse_mean, mcse_std, ess_bulk, ess_tail, rhat
   // (null = not requested); s_* = result slot of the reduction feeding a column (-1 = absent)
@@ -61,7 +67,9 @@ template <typename T> struct FastGenArgs {
   int* redo_count;
 };
 
-template <typename T>
+// QRULE = the program ends with the MCSE order-statistic rule (mcse_mode 3): only that instance carries the
+// window of sorted values and the Beta inverse, so the other programs do not pay for them.
+template <typename T, bool QRULE>
 __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenArgs<T> a) {
   using Key = typename Traits<T>::Key;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -71,6 +79,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
   unsigned* Khi = reinterpret_cast<unsigned*>(smem + FAST_OFF_KHI);
   unsigned* Klo = reinterpret_cast<unsigned*>(smem + FAST_OFF_KLO);
   double* ZC = reinterpret_cast<double*>(smem);
+  double* WIN = reinterpret_cast<double*>(smem + FAST_NCH * FAST_ROW * 8);   // [FASTGEN_WIN] sorted values, behind ZC
   unsigned char* small = smem + FAST_OFF_SMALL;
   T* cmean = reinterpret_cast<T*>(small);                  // [8]
   T* cvar = cmean + 8;                                     // [8]
@@ -279,9 +288,13 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           const int cbase = pass == 0 ? 0 : 6;
           const int fmA = (n & 1) ? n / 2 : n / 2 - 1, fmB = n / 2;   // median positions (pass 1)
           unsigned* WL = FC;
-          unsigned short* RES = WP;
-          // WANT[pos] = mask of the captures that ask for sorted position pos (second half of the dead prefixes)
-          unsigned char* WANT = reinterpret_cast<unsigned char*>(WP) + 2 * FAST_NMAX;
+          // the work list needs at most FAST_NMAX words = half of the dead counter region; RES and WANT take
+          // the rest, which leaves the dead prefix region to WIN (it must outlive the reductions)
+          unsigned short* RES = reinterpret_cast<unsigned short*>(FC + FAST_NMAX);
+          // WANT[pos] = mask of the captures that ask for sorted position pos
+          unsigned char* WANT = reinterpret_cast<unsigned char*>(FC + FAST_NMAX) + 2 * FAST_NMAX;
+          const int wlo = a.win_lo;
+          const bool fill_win = QRULE && pass == 0;
           if (ncap > 0 && w == 0) {
 #pragma unroll
             for (int i = 0; i < FAST_NMAX / (16 * 32); ++i) reinterpret_cast<uint4*>(WANT)[lane + 32 * i] = make_uint4(0, 0, 0, 0);
@@ -340,6 +353,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
                   for (int ci = 0; ci < 6; ++ci) if (m & (1u << ci)) cap[cbase + ci] = v;
                 }
               }
+              if (fill_win) {
+                double v;
+                if constexpr (FastKeys<T>::TWO) v = key_value(((unsigned long long)vhi << 32) | vlo);
+                else v = (double)key_value(vhi);
+                for (int pos = lo; pos < hi; ++pos) if ((unsigned)(pos - wlo) < (unsigned)FASTGEN_WIN) WIN[pos - wlo] = v;
+              }
               const unsigned zi = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
               RES[it >> 20] = (unsigned short)((zi >> 1) + ((zi & 1u) ? (unsigned)n : 0u));   // split z table
             }
@@ -353,6 +372,13 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
                 const unsigned m = WANT[bo[k] & 0xfffu];
                 if (m) for (int ci = 0; ci < 6; ++ci) if (m & (1u << ci)) cap[cbase + ci] = (double)x[k];
               }
+            }
+          }
+          if (fill_win) {
+#pragma unroll
+            for (int k = 0; k < FAST_EPT; ++k) {
+              const unsigned rel = (bo[k] & 0xfffu) - (unsigned)wlo;
+              if (lane + 32 * k < niter && !(shared_mask & (1u << k)) && rel < (unsigned)FASTGEN_WIN) WIN[rel] = (double)x[k];
             }
           }
 #pragma unroll
@@ -500,9 +526,27 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       if (redo) break;
     }
 
+    T mcse_q = Traits<T>::nan();
+    if (QRULE && !redo) {
+      // _mcse_quantile (mcse.jl:96-118): Beta(S p + 1, S (1 - p) + 1) quantiles at Phi(-1), Phi(+1) -> order statistics
+      __syncthreads();   // res[0] (thread 0) is visible; part[] is free
+      const double S = res[0];
+      if (S == S) {
+        const double al = S * a.mcse_p + 1.0, be = S * (1.0 - a.mcse_p) + 1.0;
+        betainc_inv_pair_block<FAST_THREADS>(al, be, 0.8413447460685429, 0.15865525393145705, part, part + 34);
+        long long u = (long long)ceil(part[34] * (double)n);
+        u = u > n ? n : (u < 1 ? 1 : u);
+        long long l = (long long)floor(part[35] * (double)n);
+        l = l < 1 ? 1 : (l > n ? n : l);
+        const long long ru = u - 1 - a.win_lo, rl = l - 1 - a.win_lo;
+        if (ru < 0 || ru >= FASTGEN_WIN || rl < 0 || rl >= FASTGEN_WIN) redo = true;   // outside the kept window: general kernel
+        else mcse_q = ((T)WIN[ru] - (T)WIN[rl]) / (T)2;
+      }
+    }
     if (redo) {
       if (tid == 0) { const int idx = atomicAdd(a.redo_count, 1); a.redo_list[idx] = (int)param; }
     } else if (tid == 0) {
+      if (QRULE) a.ess_out[param] = mcse_q;
       if (a.sum_mode) {
         // the reference calls each column stands for: src/mcse.jl:45-69, src/ess_rhat.jl:298-311, 410-420, 604-624
         if (a.col[2]) a.col[2][param] = (T)side[1] / sqrt((T)res[a.s_mean]);
@@ -511,7 +555,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
         if (a.col[5]) a.col[5][param] = jl_min<T>((T)res[a.s_tlo], (T)res[a.s_thi]);
         if (a.col[6]) a.col[6][param] = jl_max<T>((T)res[6 + 5], (T)res[6 + a.s_bulk]);
       }
-      if (a.ess_out) {
+      if (a.ess_out && !QRULE) {
         T e = (T)res[a.ess_mode == 4 ? 5 : 0];
         if (a.ess_mode == 2) e = jl_min<T>(e, (T)res[1]);
         if (a.mcse_mode == 1) e = (T)side[1] / sqrt(e);
