@@ -162,6 +162,18 @@ int mcd_summary(mcd_ctx* ctx, const void* x, int mem, int dtype,
                 unsigned fields, int autocov_method, int split_chains, int maxlag,
                 double tail_prob, int tail_prob_f64, void* out);
 
+/* Per split-chain mean and corrected variance of every parameter: the per-chain quantities that
+ * `_rhat_basic!` (src/ess_rhat.jl:387-399) and `_gelmandiag` (src/gelmandiag.jl:9-17: diag of the
+ * per-chain covariance, chain means) start from.  Outputs (chains*split_chains, params) column-major,
+ * element type = dtype; either may be NULL.   */
+int mcd_chain_moments(mcd_ctx* ctx, const void* x, int mem, int dtype,
+                      int64_t draws, int64_t chains, int64_t params, int split_chains,
+                      void* mean_out, void* var_out);
+
+/* bfmi(energy::AbstractMatrix; dims=1) (src/bfmi.jl:36-43): mean(abs2, diff(energy)) / var(energy) per
+ * chain; energy is (draws, chains) column-major, out has `chains` elements. */
+int mcd_bfmi(mcd_ctx* ctx, const void* energy, int mem, int dtype, int64_t draws, int64_t chains, void* out);
+
 /* rhat_nested: `_rhat_nested(::Val{kind}, x, chain_inds; split_chains)` +
  * `_rhat_nested_basic!` (src/rhat_nested.jl:83-188).  chain_inds is a HOST array,
  * column-major (chains_per_super x nsuper), 0-based chain indices, as produced by

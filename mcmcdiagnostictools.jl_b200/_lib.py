@@ -41,6 +41,8 @@ SIGNATURES = {
     "mcd_ess_estimator": (_int, _SHAPE + [_int, _dbl, _int, _int, _int, _int, _int, _vp]),
     "mcd_mcse": (_int, _SHAPE + [_int, _dbl, _int, _int, _int, _int, _vp]),
     "mcd_summary": (_int, _SHAPE + [C.c_uint, _int, _int, _int, _dbl, _int, _vp]),
+    "mcd_chain_moments": (_int, _SHAPE + [_int, _vp, _vp]),
+    "mcd_bfmi": (_int, [_vp, _vp, _int, _int, _i64, _i64, _vp]),
     "mcd_rhat_nested": (_int, _SHAPE + [_vp, _i64, _i64, _int, _int, _vp]),
     "mcd_tiedrank": (_int, _SHAPE + [_vp]),
     "mcd_rank_normalize": (_int, _SHAPE + [_vp]),

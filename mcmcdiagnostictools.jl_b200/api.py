@@ -38,10 +38,12 @@ __all__ = [
     "Context", "get_context", "tiedrank", "rank_normalize", "fold_around_median",
     "generate_ar1", "ESSRhat", "summary", "SUMMARY_FIELDS",
     "gewekediag", "heideldiag", "GewekeResult", "HeidelResult",
+    "bfmi", "gelmandiag", "GelmanResult", "chain_moments",
 ]
 
 ESSRhat = namedtuple("ESSRhat", ["ess", "rhat"])
 GewekeResult = namedtuple("GewekeResult", ["zscore", "pvalue"])
+GelmanResult = namedtuple("GelmanResult", ["psrf", "psrfci"])
 HeidelResult = namedtuple("HeidelResult", ["burnin", "stationarity", "pvalue", "mean", "halfwidth", "test"])
 # columns of `summary`, in the bit order of MCD_SUM_* (include/mcmcdiag_b200.h)
 SUMMARY_FIELDS = ("mean", "std", "mcse_mean", "mcse_std", "ess_bulk", "ess_tail", "rhat")
@@ -694,3 +696,100 @@ def heideldiag(x, *, alpha=Fraction(1, 20), eps=0.1, start=1, ctx=None, **kwargs
         return HeidelResult(int(out.burnin[0]), bool(out.stationarity[0]), T(out.pvalue[0]), T(out.mean[0]),
                             T(out.halfwidth[0]), bool(out.test[0]))
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# the same moment kernels behind a different combine
+# ---------------------------------------------------------------------------------------
+def chain_moments(samples, *, split_chains=1, ctx=None):
+    """Mean and corrected variance of every (split) chain of every parameter, as two arrays of shape
+    `(chains * split_chains, params)`: what `_rhat_basic!` (src/ess_rhat.jl:387-399) and `_gelmandiag`
+    (src/gelmandiag.jl:9-17) start from."""
+    _check_split(split_chains)
+    a = _Arr(samples, min_ndim=2)
+    if a.missing is not None and a.missing.any():
+        raise ArgumentError("chain_moments does not take missing values")
+    ctx = a.context(ctx)
+    nch = a.chains * int(split_chains)
+    if a.is_torch:
+        import torch
+        mk = lambda: torch.empty((a.nparams, nch), dtype=a.torch_dtype, device=a.torch_device)
+    else:
+        mk = lambda: np.empty((a.nparams, nch), dtype=a.dtype)
+    mean, var = mk(), mk()
+    rc = ctx._lib.mcd_chain_moments(ctx._h, C.c_void_p(a.ptr), a.mem, a.code, a.draws, a.chains, a.nparams,
+                                    int(split_chains), a.out_ptr(mean), a.out_ptr(var))
+    ctx.check(rc)
+    return mean.T, var.T          # (nch, params): the library writes column-major
+
+
+def bfmi(energy, *, dims=1, ctx=None):
+    """`bfmi(energy::AbstractVector)` / `bfmi(energy::AbstractMatrix; dims=1)` (src/bfmi.jl:36-43):
+    `mean(abs2, diff(energy)) / var(energy)` per chain.  `dims` is the (1-based, as in the reference)
+    dimension holding the draws."""
+    is_torch = type(energy).__module__.split(".")[0] == "torch"
+    nd = energy.ndim if hasattr(energy, "ndim") else np.asarray(energy).ndim
+    if nd == 1:
+        e2 = energy.reshape(-1, 1) if is_torch else np.asarray(energy).reshape(-1, 1)
+    elif nd == 2:
+        if dims not in (1, 2):
+            raise ArgumentError("dims must be 1 or 2")
+        e2 = energy if dims == 1 else (energy.T if not is_torch else energy.t())
+        if not is_torch:
+            e2 = np.asarray(e2)
+    else:
+        raise ArgumentError("energy must be a vector or a matrix")
+    a = _Arr(e2.reshape(e2.shape[0], e2.shape[1], 1), min_ndim=3)   # (draws, chains, 1): chains are contiguous columns
+    ctx = a.context(ctx)
+    if a.is_torch:
+        import torch
+        out = torch.empty(a.chains, dtype=a.torch_dtype, device=a.torch_device)
+    else:
+        out = np.empty(a.chains, dtype=a.dtype)
+    rc = ctx._lib.mcd_bfmi(ctx._h, C.c_void_p(a.ptr), a.mem, a.code, a.draws, a.chains, a.out_ptr(out))
+    ctx.check(rc)
+    if nd == 1:
+        return out[0] if not a.is_torch else out.reshape(())
+    return out
+
+
+def gelmandiag(samples, *, alpha=0.05, ctx=None):
+    """`gelmandiag(samples::AbstractArray{<:Real,3}; alpha=0.05) -> (psrf, psrfci)` (src/gelmandiag.jl:1-76):
+    Gelman-Rubin-Brooks potential scale reduction factors and their upper confidence limits.  Only the
+    diagonals of the within / between covariance matrices are needed, i.e. the per-chain means and
+    variances, which come from the device (`mcd_chain_moments`); the combine is O(chains * params)."""
+    from scipy import stats
+    nd = samples.ndim if hasattr(samples, "ndim") else np.asarray(samples).ndim
+    if nd != 3:
+        raise ArgumentError("`samples` must have shape (draws, chains, parameters)")
+    niters, nchains = int(samples.shape[0]), int(samples.shape[1])
+    if not nchains > 1:
+        raise RuntimeError("Gelman diagnostic requires at least 2 chains")
+    mean, var = chain_moments(samples, split_chains=1, ctx=ctx)
+    to_np = lambda v: v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+    psibar = to_np(mean).astype(np.float64)       # (chains, params)
+    s2 = to_np(var).astype(np.float64)
+    rfixed = (niters - 1) / niters
+    rrandomscale = (nchains + 1) / (nchains * niters)
+    with np.errstate(all="ignore"):
+        w = s2.mean(axis=0)
+        b = niters * psibar.var(axis=0, ddof=1)
+        psibar2 = psibar.mean(axis=0)
+
+        def cov(u, v):
+            return ((u - u.mean(axis=0)) * (v - v.mean(axis=0))).sum(axis=0) / (nchains - 1)
+
+        var_w = s2.var(axis=0, ddof=1) / nchains
+        var_b = (2 / (nchains - 1)) * b ** 2
+        var_wb = (niters / nchains) * (cov(s2, psibar ** 2) - 2 * psibar2 * cov(s2, psibar))
+        V = rfixed * w + rrandomscale * b
+        var_V = rfixed ** 2 * var_w + rrandomscale ** 2 * var_b + 2 * rfixed * rrandomscale * var_wb
+        df = 2 * V ** 2 / var_V
+        W_df = 2 * w ** 2 / var_w
+        correction = (df + 3) / (df + 1)
+        rrandom = rrandomscale * b / w
+        psrf = np.sqrt(correction * (rfixed + rrandom))
+        q = stats.f.ppf(1 - alpha / 2, nchains - 1, W_df)
+        upper = np.where(np.isnan(rrandom), rrandom, rrandom * q)
+        psrfci = np.sqrt(correction * (rfixed + upper))
+    return GelmanResult(psrf, psrfci)

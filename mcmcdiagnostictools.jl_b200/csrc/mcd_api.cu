@@ -214,6 +214,57 @@ __global__ void __launch_bounds__(256) moments_kernel(const T* __restrict__ x, l
   }
 }
 
+// Mean and corrected variance of every split chain of every parameter (the per-chain quantities of
+// src/ess_rhat.jl:387-399 and of src/gelmandiag.jl:9-17), one warp per (parameter, split chain), two
+// passes in double.  Outputs are (nch, params) column-major.
+template <typename T>
+__global__ void __launch_bounds__(256) chain_moments_kernel(const T* __restrict__ x, long long params, SplitGeom g,
+                                                           T* __restrict__ mean_out, T* __restrict__ var_out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long item = warp0; item < params * g.nch; item += nwarps) {
+    const long long p = item / g.nch;
+    const int j = (int)(item - p * g.nch);
+    const T* src = x + p * (long long)g.n + g.chain_start(j);
+    double s = 0.0;
+    for (int t = lane; t < g.niter; t += 32) s += (double)__ldg(&src[t]);
+    s = warp_sum(s);
+    const T m = (T)(s / (double)g.niter);
+    double q = 0.0;
+    for (int t = lane; t < g.niter; t += 32) { const T d = __ldg(&src[t]) - m; q = fma((double)d, (double)d, q); }
+    q = warp_sum(q);
+    if (lane == 0) {
+      if (mean_out) mean_out[item] = m;
+      if (var_out) var_out[item] = (T)(q / (double)(g.niter - 1));
+    }
+  }
+}
+
+// bfmi (src/bfmi.jl:36-43): mean(abs2, diff(energy)) / var(energy) per chain, one warp per chain.
+template <typename T>
+__global__ void __launch_bounds__(256) bfmi_kernel(const T* __restrict__ e, long long draws, long long chains,
+                                                  T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long c = warp0; c < chains; c += nwarps) {
+    const T* src = e + c * draws;
+    double s = 0.0;
+    for (long long t = lane; t < draws; t += 32) s += (double)__ldg(&src[t]);
+    const T m = (T)(warp_sum(s) / (double)draws);
+    double q = 0.0, d2 = 0.0;
+    for (long long t = lane; t < draws; t += 32) {
+      const T v = __ldg(&src[t]);
+      const T d = v - m;
+      q = fma((double)d, (double)d, q);
+      if (t + 1 < draws) { const T df = __ldg(&src[t + 1]) - v; d2 = fma((double)df, (double)df, d2); }
+    }
+    q = warp_sum(q); d2 = warp_sum(d2);
+    if (lane == 0) out[c] = (T)(d2 / (double)(draws - 1)) / (T)(q / (double)(draws - 1));
+  }
+}
+
 // log10(oftype(one(T), ntotal)) (src/ess_rhat.jl:514), correctly rounded: glibc's double
 // log10 is not (log10(40.0) is off by one ulp), so evaluate in long double and round once.
 template <typename T> static T rel_ess_max_of(long long ntotal) {
@@ -787,6 +838,75 @@ static int setup_ess(mcd_ctx* ctx, Program& pg, long long draws, int split, int 
   return MCD_OK;
 }
 
+// Secondary entry points: plain moment kernels.  Host input is staged in parameter
+// chunks through the first staging buffer (synchronously: these calls are HBM/PCIe-trivial).
+template <typename T>
+static int chain_moments_t(mcd_ctx* ctx, const void* x, int mem, long long draws, long long chains, long long params,
+                           int split, void* mean_out, void* var_out) {
+  SplitGeom g((int)draws, (int)chains, split);
+  if (g.niter < 1) return fail(ctx, MCD_EINVAL, "fewer draws than split chains");
+  CU(cudaSetDevice(ctx->device));
+  auto launch = [&](const T* dx, long long cnt, T* dm, T* dv) -> int {
+    const long long warps = cnt * g.nch;
+    const unsigned grid = (unsigned)std::min<long long>((warps + 7) / 8, (long long)ctx->sm_count * 32);
+    chain_moments_kernel<T><<<grid ? grid : 1, 256, 0, ctx->stream>>>(dx, cnt, g, dm, dv);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    return MCD_OK;
+  };
+  if (params == 0) return MCD_OK;
+  if (mem == MCD_DEVICE) return launch((const T*)x, params, (T*)mean_out, (T*)var_out);
+  if (mem != MCD_HOST) return fail(ctx, MCD_EINVAL, "bad mem kind %d", mem);
+  const size_t slab_bytes = (size_t)g.n * sizeof(T), row = (size_t)g.nch * sizeof(T);
+  long long chunk = std::max<long long>(1, ctx->h2d_chunk_bytes / (long long)slab_bytes);
+  chunk = std::min(chunk, params);
+  int rc = ensure_cap(ctx, &ctx->stage[0], &ctx->stage_cap[0], (size_t)chunk * slab_bytes);
+  if (rc) return rc;
+  rc = ensure_cap(ctx, &ctx->d_out, &ctx->out_cap, 2 * (size_t)chunk * row);
+  if (rc) return rc;
+  T* dm = (T*)ctx->d_out; T* dv = dm + chunk * g.nch;
+  for (long long done = 0; done < params; done += chunk) {
+    const long long cnt = std::min(chunk, params - done);
+    CU(cudaMemcpyAsync(ctx->stage[0], (const char*)x + (size_t)done * slab_bytes, (size_t)cnt * slab_bytes,
+                       cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += cnt * (long long)slab_bytes;
+    rc = launch((const T*)ctx->stage[0], cnt, dm, dv);
+    if (rc) return rc;
+    if (mean_out) CU(cudaMemcpyAsync((char*)mean_out + (size_t)done * row, dm, (size_t)cnt * row, cudaMemcpyDeviceToHost, ctx->stream));
+    if (var_out) CU(cudaMemcpyAsync((char*)var_out + (size_t)done * row, dv, (size_t)cnt * row, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->d2h_bytes += 2 * cnt * (long long)row;
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return MCD_OK;
+}
+
+template <typename T>
+static int bfmi_t(mcd_ctx* ctx, const void* e, int mem, long long draws, long long chains, void* out) {
+  CU(cudaSetDevice(ctx->device));
+  const T* de = (const T*)e;
+  T* dout = (T*)out;
+  const size_t bytes = (size_t)draws * chains * sizeof(T);
+  if (mem == MCD_HOST) {
+    int rc = ensure_cap(ctx, &ctx->stage[0], &ctx->stage_cap[0], bytes);
+    if (rc) return rc;
+    rc = ensure_cap(ctx, &ctx->d_out, &ctx->out_cap, (size_t)chains * sizeof(T));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->stage[0], e, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += (long long)bytes;
+    de = (const T*)ctx->stage[0]; dout = (T*)ctx->d_out;
+  } else if (mem != MCD_DEVICE) return fail(ctx, MCD_EINVAL, "bad mem kind %d", mem);
+  const unsigned grid = (unsigned)std::min<long long>((chains + 7) / 8, (long long)ctx->sm_count * 32);
+  bfmi_kernel<T><<<grid ? grid : 1, 256, 0, ctx->stream>>>(de, draws, chains, dout);
+  CU(cudaGetLastError());
+  ++ctx->launches;
+  if (mem == MCD_HOST) {
+    CU(cudaMemcpyAsync(out, dout, (size_t)chains * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->d2h_bytes += chains * (long long)sizeof(T);
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return MCD_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------
@@ -1107,6 +1227,32 @@ int mcd_rank_normalize(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t 
 int mcd_fold_around_median(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains,
                            int64_t params, void* out) {
   return transform_call(ctx, x, mem, dtype, draws, chains, params, TR_FOLD, dtype == MCD_F64 ? 8 : 4, out);
+}
+
+int mcd_chain_moments(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,
+                      int split_chains, void* mean_out, void* var_out) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->err.clear();
+  if (!mean_out && !var_out) return fail(ctx, MCD_EINVAL, "both outputs are NULL");
+  if (draws <= 0 || chains <= 0 || params < 0) return fail(ctx, MCD_EINVAL, "draws and chains must be positive");
+  if (split_chains < 1) return fail(ctx, MCD_EINVAL, "split_chains must be >= 1");
+  if (draws * chains > (1ll << 30)) return fail(ctx, MCD_EUNSUPPORTED, "slab too large (draws*chains > 2^30)");
+  if (params > 0 && !x) return fail(ctx, MCD_EINVAL, "x is NULL");
+  if (dtype == MCD_F64) return chain_moments_t<double>(ctx, x, mem, draws, chains, params, split_chains, mean_out, var_out);
+  if (dtype == MCD_F32) return chain_moments_t<float>(ctx, x, mem, draws, chains, params, split_chains, mean_out, var_out);
+  return fail(ctx, MCD_EINVAL, "bad dtype %d", dtype);
+}
+
+int mcd_bfmi(mcd_ctx* ctx, const void* energy, int mem, int dtype, int64_t draws, int64_t chains, void* out) {
+  if (!ctx) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->err.clear();
+  if (!energy || !out) return fail(ctx, MCD_EINVAL, "NULL argument");
+  if (draws <= 0 || chains <= 0) return fail(ctx, MCD_EINVAL, "draws and chains must be positive");
+  if (dtype == MCD_F64) return bfmi_t<double>(ctx, energy, mem, draws, chains, out);
+  if (dtype == MCD_F32) return bfmi_t<float>(ctx, energy, mem, draws, chains, out);
+  return fail(ctx, MCD_EINVAL, "bad dtype %d", dtype);
 }
 
 int mcd_generate_ar1(mcd_ctx* ctx, int dtype, int64_t draws, int64_t chains, int64_t params, int64_t param_offset,

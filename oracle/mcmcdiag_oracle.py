@@ -823,3 +823,56 @@ def heideldiag(x, alpha=Fraction(1, 20), eps=0.1, start=1, **kw):
     passed = bool(halfwidth / abs(ybar) <= eps)
     return {"burnin": i + start - 2, "stationarity": converged, "pvalue": pvalue, "mean": ybar,
             "halfwidth": T(halfwidth), "test": passed}
+
+
+# ----------------------------------------------------------------------------------------
+# bfmi (src/bfmi.jl:36-43), gelmandiag (src/gelmandiag.jl:1-76)
+# ----------------------------------------------------------------------------------------
+def bfmi(energy, dims=1):
+    e = np.asarray(energy)
+    T = _float_dtype(e)
+    e = e.astype(T)
+    if e.ndim == 1:
+        return T(np.mean(np.diff(e) ** 2, dtype=T) / np.var(e, ddof=1, dtype=T))
+    ax = dims - 1
+    return (np.mean(np.diff(e, axis=ax) ** 2, axis=ax, dtype=T) / np.var(e, axis=ax, ddof=1, dtype=T)).astype(T)
+
+
+def gelmandiag(psi, alpha=0.05):
+    """Line-by-line restatement of `_gelmandiag` (full covariance matrices, then their diagonals)."""
+    from scipy import stats
+    psi = np.asarray(psi, dtype=np.float64)
+    niters, nchains, nparams = psi.shape
+    if not nchains > 1:
+        raise RuntimeError("Gelman diagnostic requires at least 2 chains")
+    rfixed = (niters - 1) / niters
+    rrandomscale = (nchains + 1) / (nchains * niters)
+    S2 = [np.atleast_2d(np.cov(psi[:, i, :], rowvar=False)) for i in range(nchains)]
+    W = sum(S2) / nchains
+    psibar = psi.mean(axis=0)                                   # (chains, params)
+    B = niters * np.atleast_2d(np.cov(psibar, rowvar=False))
+    w, b = np.diag(W), np.diag(B)
+    s2 = np.stack([np.diag(S) for S in S2], axis=0)             # (chains, params)
+    psibar2 = psibar.mean(axis=0)
+
+    def cov_diag(u, v):
+        return np.array([np.cov(u[:, j], v[:, j])[0, 1] for j in range(nparams)])
+
+    with np.errstate(all="ignore"):
+        var_w = s2.var(axis=0, ddof=1) / nchains
+        var_b = (2 / (nchains - 1)) * b ** 2
+        var_wb = (niters / nchains) * (cov_diag(s2, psibar ** 2) - 2 * psibar2 * cov_diag(s2, psibar))
+        V = rfixed * w + rrandomscale * b
+        var_V = rfixed ** 2 * var_w + rrandomscale ** 2 * var_b + 2 * rfixed * rrandomscale * var_wb
+        df = 2 * V ** 2 / var_V
+        W_df = 2 * w ** 2 / var_w
+        est = np.empty(nparams)
+        up = np.empty(nparams)
+        for i in range(nparams):
+            correction = (df[i] + 3) / (df[i] + 1)
+            rrandom = rrandomscale * b[i] / w[i]
+            est[i] = np.sqrt(correction * (rfixed + rrandom))
+            if not np.isnan(rrandom):
+                rrandom *= stats.f.ppf(1 - alpha / 2, nchains - 1, W_df[i])
+            up[i] = np.sqrt(correction * (rfixed + rrandom))
+    return {"psrf": est, "psrfci": up}

@@ -85,3 +85,50 @@ def test_callers_accept_device_tensors(mcd, o):
     assert np.array_equal(g_h.zscore, g_d.zscore)
     h_h, h_d = mcd.heideldiag(x), mcd.heideldiag(torch.as_tensor(x, device="cuda"))
     assert np.array_equal(h_h.burnin, h_d.burnin) and np.array_equal(h_h.halfwidth, h_d.halfwidth)
+
+
+BFMI_ENERGY = [42, 44, 45, 46, 42, 43, 36, 36, 31, 36, 36, 32, 36, 31, 31, 29, 29, 30, 25, 26, 29, 29, 27, 30, 31, 29]
+
+
+def test_bfmi_golden_values_and_parity(mcd, o):
+    """test/bfmi.jl: 0.6 by hand, 0.2406937229 from ArviZ; matrix form, dims=2; Float32; device tensors."""
+    import torch
+    assert np.isclose(mcd.bfmi([1, 2, 3, 4]), 0.6)
+    assert np.isclose(mcd.bfmi(BFMI_ENERGY), 0.2406937229, rtol=1e-9)
+    multi = np.repeat(np.asarray(BFMI_ENERGY, dtype=float)[:, None], 4, axis=1)
+    assert np.allclose(mcd.bfmi(multi), 0.2406937229, rtol=1e-9)
+    assert np.allclose(mcd.bfmi(multi), mcd.bfmi(multi.T, dims=2))
+    e = np.random.default_rng(3).standard_normal((1000, 7)).cumsum(axis=0) * 0.1 + np.random.default_rng(4).standard_normal((1000, 7))
+    assert np.allclose(mcd.bfmi(e), o.bfmi(e), rtol=1e-10)
+    assert np.allclose(mcd.bfmi(e.astype(np.float32)), o.bfmi(e.astype(np.float32)), rtol=1e-4)
+    assert np.allclose(mcd.bfmi(torch.as_tensor(e, device="cuda")).cpu().numpy(), o.bfmi(e), rtol=1e-10)
+
+
+def test_chain_moments_and_gelmandiag(mcd, o):
+    rng = np.random.default_rng(21)
+    x = o.ar1(0.4, 0.9, 301, 5, 9, rng=rng)
+    x[:, 0, 0] += 2.0
+    x[:, :, 3] = 1.5                                      # constant parameter: NaN, as in the reference
+    for split in (1, 2, 3):
+        m, v = mcd.chain_moments(x, split_chains=split)
+        sp = np.stack([o.copyto_split(x[:, :, p], split) for p in range(x.shape[2])], axis=2)   # (niter, nch, P)
+        assert m.shape == (5 * split, 9)
+        assert np.allclose(m, sp.mean(axis=0), rtol=1e-12, atol=1e-15)
+        assert np.allclose(v, sp.var(axis=0, ddof=1), rtol=1e-11, atol=1e-30)
+    got, want = mcd.gelmandiag(x), o.gelmandiag(x)
+    assert got.psrf.dtype == np.float64 and got.psrf.shape == (9,)
+    assert np.allclose(got.psrf, want["psrf"], rtol=1e-9, equal_nan=True)
+    assert np.allclose(got.psrfci, want["psrfci"], rtol=1e-8, equal_nan=True)
+    assert got.psrf[0] > 1.2
+    got2, want2 = mcd.gelmandiag(x, alpha=0.2), o.gelmandiag(x, alpha=0.2)
+    assert np.allclose(got2.psrfci, want2["psrfci"], rtol=1e-8, equal_nan=True)
+    with pytest.raises(RuntimeError):
+        mcd.gelmandiag(x[:, :1, :])
+    ctx = mcd.get_context(0)
+    ctx.set_option("h2d_chunk_bytes", 3 * 301 * 5 * 8)    # several staged chunks
+    try:
+        m2, v2 = mcd.chain_moments(x, split_chains=2)
+    finally:
+        ctx.set_option("h2d_chunk_bytes", 256 << 20)
+    m1, v1 = mcd.chain_moments(x, split_chains=2)
+    assert np.array_equal(m1, m2) and np.array_equal(v1, v2)

@@ -371,3 +371,30 @@ def test_gewekediag_heideldiag_oracle_behaviour():
     assert o.gewekediag(y)["pvalue"] > 0.01 and o.heideldiag(y)["stationarity"]
     bad = y + np.linspace(3, 0, 2000) ** 2
     assert o.gewekediag(bad)["pvalue"] < 1e-6 and not o.heideldiag(bad)["stationarity"]
+
+
+BFMI_ENERGY = [42, 44, 45, 46, 42, 43, 36, 36, 31, 36, 36, 32, 36, 31, 31, 29, 29, 30, 25, 26, 29, 29, 27, 30, 31, 29]
+
+
+def test_bfmi_golden_values():
+    """test/bfmi.jl:2-43: the hand value 0.6 and ArviZ's 0.2406937229 for the 26-draw energy series."""
+    from oracle import mcmcdiag_oracle as o
+    assert np.isclose(o.bfmi([1, 2, 3, 4]), 0.6)
+    assert np.isclose(o.bfmi(BFMI_ENERGY), 0.2406937229, rtol=1e-9)
+    multi = np.repeat(np.asarray(BFMI_ENERGY, dtype=float)[:, None], 4, axis=1)
+    assert np.allclose(o.bfmi(multi), 0.2406937229, rtol=1e-9)
+    assert np.allclose(o.bfmi(multi), o.bfmi(multi.T, dims=2))
+
+
+def test_gelmandiag_oracle_behaviour():
+    """test/gelmandiag.jl: shapes / types / exceptions; PSRF ~ 1 for IID chains, > 1.2 when chains disagree."""
+    from oracle import mcmcdiag_oracle as o
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((100, 2, 4))
+    r = o.gelmandiag(x)
+    assert r["psrf"].shape == (4,) and r["psrf"].dtype == np.float64 and r["psrfci"].shape == (4,)
+    assert np.all(np.abs(r["psrf"] - 1) < 0.1) and np.all(r["psrfci"] >= r["psrf"])
+    with pytest.raises(RuntimeError):
+        o.gelmandiag(x[:, :1, :])
+    y = rng.standard_normal((500, 4, 2)); y[:, 0, 0] += 3.0
+    assert o.gelmandiag(y)["psrf"][0] > 1.2 and abs(o.gelmandiag(y)["psrf"][1] - 1) < 0.05
