@@ -48,6 +48,7 @@ struct mcd_ctx {
   long long workspace_bytes = 6ll << 30;
   int bucket_limit = 64;
   int fast_pad_smem = 0;   // developer knob: extra dynamic shared memory (lowers CTAs/SM)
+  int slab_wide = 1;       // developer knob: 512-thread general kernel for slabs that fit one CTA per SM only
   int fast_grid_mult = 0;  // developer knob: 0 = one CTA per parameter, k = persistent grid of k * 2 * SMs CTAs
   // stats
   long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -328,7 +329,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Lay the slab kernel's shared memory out; returns total bytes.
 template <typename T>
-static size_t slab_layout(SlabArgs<T>& a, const Program& pg) {
+static size_t slab_layout(SlabArgs<T>& a, const Program& pg, int threads = SLAB_THREADS) {
   const size_t ts = sizeof(T);
   const int n = a.g.n;
   size_t off = 0;
@@ -338,13 +339,13 @@ static size_t slab_layout(SlabArgs<T>& a, const Program& pg) {
   const bool alias_xy = pg.nsteps == 1 && pg.combine == CB_PLAIN;
   a.offY = alias_xy ? a.offX : take((size_t)n * ts);
   a.offK = take((size_t)n * ts);
-  a.offCNT = take((size_t)(a.nbuckets + SLAB_THREADS) * 4);
+  a.offCNT = take((size_t)(a.nbuckets + threads) * 4);
   size_t view_bytes = off - (size_t)a.offK;
   a.offCM = take((size_t)a.g.nch * ts);
   a.offCV = take((size_t)a.g.nch * ts);
   a.offGAM = take((size_t)(a.maxlag + 1 + LAG_BATCH) * ts);
   a.offGSUM = take(pg.method == MCD_AUTOCOV_FFT ? (size_t)(a.maxlag + 1) * 8 : 0);
-  size_t part = (size_t)(SLAB_THREADS / 32) * LAG_BATCH;
+  size_t part = (size_t)(threads / 32) * LAG_BATCH;
   if ((size_t)(2 * pg.nsuper) > part) part = (size_t)(2 * pg.nsuper);
   a.offPART = take(part * 8);
   a.offFFT = a.offK;
@@ -388,6 +389,12 @@ static int run_slab(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
     const size_t s2 = slab_layout<T>(a, pg);
     if (s2 <= two_cta) smem = s2; else { a.nbuckets = full; smem = slab_layout<T>(a, pg); }
   }
+  // a slab that leaves room for one CTA per SM only gets 16 warps instead of 8 to hide latency
+  int threads = SLAB_THREADS;
+  if (smem > two_cta && g.n >= 4096 && !redo_list && ctx->slab_wide) {
+    const size_t s512 = slab_layout<T>(a, pg, 512);
+    if (s512 <= (size_t)ctx->smem_optin) { threads = 512; smem = s512; } else smem = slab_layout<T>(a, pg);
+  }
   if (smem > (size_t)ctx->smem_optin) return MCD_OK;  // not handled: caller uses the large path
 
   const int dtype = sizeof(T) == 8 ? MCD_F64 : MCD_F32;
@@ -403,12 +410,13 @@ static int run_slab(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   }
   if (pg.chain_inds) a.chain_inds = ctx->d_chain_inds;
 
-  auto kern = slab_kernel<T, SLAB_THREADS>;
+  const bool three = 3 * (smem + 1024) <= (size_t)ctx->smem_optin + 1024;   // three CTAs of this slab fit an SM
+  auto kern = threads == 512 ? slab_kernel_wide<T, 512> : (three ? slab_kernel<T, SLAB_THREADS> : slab_kernel_two<T, SLAB_THREADS>);
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long grid = std::min<long long>(params, 1ll << 30);
   if (redo_list) grid = std::min<long long>(grid, 2ll * ctx->sm_count);
   if (grid > 0) {
-    kern<<<(unsigned)grid, SLAB_THREADS, smem, ctx->stream>>>(a);
+    kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
   }
@@ -998,6 +1006,7 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   else if (k == "workspace_bytes") { if (value < (1 << 20)) return fail(ctx, MCD_EINVAL, "workspace_bytes >= 1 MiB"); ctx->workspace_bytes = value; }
   else if (k == "fast_pad_smem") { ctx->fast_pad_smem = (int)value; }
   else if (k == "fast_grid_mult") { ctx->fast_grid_mult = (int)value; }
+  else if (k == "slab_wide") ctx->slab_wide = value ? 1 : 0;
   else if (k == "sort_bucket_limit") { if (value < 0) return fail(ctx, MCD_EINVAL, "sort_bucket_limit >= 0"); ctx->bucket_limit = (int)value; }
   else return fail(ctx, MCD_EINVAL, "unknown option '%s'", key);
   return MCD_OK;

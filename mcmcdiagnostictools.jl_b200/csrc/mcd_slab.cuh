@@ -688,7 +688,7 @@ __device__ Result reduce_nested(const T* Y, const SlabArgs<T>& a, unsigned char*
 
 // ---- the kernel ---------------------------------------------------------------------------
 template <typename T, int THREADS>
-__global__ void __launch_bounds__(THREADS) slab_kernel(const SlabArgs<T> a) {
+__device__ __forceinline__ void slab_body(const SlabArgs<T>& a) {
   extern __shared__ __align__(16) unsigned char smem[];
   T* X = reinterpret_cast<T*>(smem + a.offX);
   T* Y = reinterpret_cast<T*>(smem + a.offY);
@@ -864,5 +864,15 @@ __global__ void __launch_bounds__(THREADS) slab_kernel(const SlabArgs<T> a) {
     __syncthreads();
   }
 }
+
+// Three entry points over the same body, chosen by how many CTAs the slab lets an SM hold: <= 80 registers
+// so that three or more fit (small slabs), 128 registers without spills for two, and 512 threads for slabs
+// that fit one CTA per SM only (16 warps hide more latency).
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, 3) slab_kernel(const SlabArgs<T> a) { slab_body<T, THREADS>(a); }
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) slab_kernel_two(const SlabArgs<T> a) { slab_body<T, THREADS>(a); }
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) slab_kernel_wide(const SlabArgs<T> a) { slab_body<T, THREADS>(a); }
 
 }  // namespace mcd
