@@ -83,3 +83,21 @@ def test_full_size_sentinels(big):
     xs = sub[:, :, [7, 11]].cpu().numpy()
     So, Ro = o.ess_rhat(xs)
     assert np.allclose(Ss[[7, 11]].cpu().numpy(), So, rtol=1e-8) and np.allclose(Rs[[7, 11]].cpu().numpy(), Ro, rtol=1e-8)
+
+
+def test_full_size_summary_equals_separate_calls(big):
+    """The fused seven-column summary over all 1e6 parameters gives the bits of the separate calls
+    (ESS / R-hat / MCSE columns) and the rank-kind results the fixture computed."""
+    import torch
+    m, x, S, R = big
+    out = m.summary(x)
+    assert torch.equal(out["ess_bulk"], S) and torch.equal(out["rhat"], R)
+    assert torch.equal(out["ess_tail"], m.ess(x, kind="tail"))
+    assert torch.equal(out["mcse_mean"], m.mcse(x, kind="mean"))
+    assert torch.equal(out["mcse_std"], m.mcse(x, kind="std"))
+    # mean / std against torch on a slice (different summation order: tolerance, not bits)
+    sl = x[:, :, :50_000].reshape(4000, -1) if x.shape[0] == 4000 else x[:, :, :50_000].reshape(-1, 50_000)
+    assert torch.allclose(out["mean"][:50_000], sl.mean(dim=0), rtol=0, atol=1e-13)
+    assert torch.allclose(out["std"][:50_000], sl.std(dim=0), rtol=1e-12, atol=0)
+    ctx = m.get_context(0)
+    assert ctx.stat("redo_count") == 0 and ctx.stat("last_path") == 3
