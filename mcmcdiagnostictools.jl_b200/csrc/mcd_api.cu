@@ -534,7 +534,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   CU(cudaMemsetAsync(ctx->d_redo, 0, sizeof(int), ctx->stream));
   if (lean) {
     const size_t smem = fast_smem_bytes<T>(pg.maxlag) + (size_t)ctx->fast_pad_smem;
-    auto kern = fast_kernel<T>;
+    auto kern = g.niter > 32 * (FAST_EPT - 1) ? fast_kernel<T, true> : fast_kernel<T, false>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = ctx->fast_grid_mult ? (unsigned)std::min<long long>(params, (long long)ctx->fast_grid_mult * 2 * ctx->sm_count) : (unsigned)params;
     kern<<<grid, FAST_THREADS, smem, ctx->stream>>>(a);

@@ -153,7 +153,9 @@ __device__ __noinline__ unsigned resolve_exact(const unsigned* Khi, const unsign
   return less | (eq << 16);
 }
 
-template <typename T>
+// LONG = every split chain has more than 480 draws: only the last of a thread's 16 slots can be empty, so
+// the validity test of the other 15 folds away at compile time (the canonical 500-draw split chains).
+template <typename T, bool LONG>
 __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T> a) {
   using Key = typename Traits<T>::Key;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int niter = a.niter;
+  auto live = [&](int k) -> bool { return LONG ? (k < FAST_EPT - 1 || lane + 32 * (FAST_EPT - 1) < niter) : (lane + 32 * k < niter); };
   if (tid == 0) { Khi[FAST_SENT] = 0xffffffffu; Khi[FAST_SENT + 1] = 0; }   // sentinel (unused by the list resolve); list length
 
   for (long long param = blockIdx.x; param < a.params; param += gridDim.x) {
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
 #pragma unroll
     for (int k = 0; k < FAST_EPT; ++k) {
       const int t = lane + 32 * k;
-      x[k] = t < niter ? __ldg(&src[t]) : (T)0;
+      x[k] = live(k) ? __ldg(&src[t]) : (T)0;
     }
     double ess = (double)Traits<T>::nan(), rhat_bulk = 0.0, rhat_tail = 0.0;
     bool redo = false;
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
           int bad = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            if (lane + 32 * k < niter) {
+            if (live(k)) {
               const T v = x[k];
               bad |= (v != v);
               lmin = v < lmin ? v : lmin;
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
           unsigned maxoff = 0, shared_mask = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            if (lane + 32 * k < niter) {
+            if (live(k)) {
               const unsigned fb = (unsigned)bucket_of<T>(x[k], (double)vmin, (double)scale, FAST_FINE);
               const unsigned sh = (fb & 7u) * 4u;
               const unsigned off = (atomicAdd(&FC[fb >> 3], 1u << sh) >> sh) & 15u;
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
           // ---- position: start of the fine bucket, population, own slot; shared buckets scatter ----
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            const bool valid = lane + 32 * k < niter;
+            const bool valid = live(k);
             const unsigned fb = bo[k] & 0xffffu, off = bo[k] >> 16;
             const unsigned word = fb >> 3, sh = (fb & 7u) * 4u;
             const unsigned fw = FC[word];
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
 #pragma unroll
             for (int k = 0; k < FAST_EPT; ++k) {
               const int st = (int)(bo[k] & 0xfffu);
-              if (lane + 32 * k < niter && !(shared_mask & (1u << k))) {
+              if (live(k) && !(shared_mask & (1u << k))) {
                 if (st == mA) thr[0] = (double)x[k];
                 if (st == mB) thr[1] = (double)x[k];
               }
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
           for (int k = 0; k < FAST_EPT; ++k)
             bo[k] = (shared_mask & (1u << k)) ? (unsigned)RES[k * FAST_THREADS + tid] : (bo[k] & 0xfffu);
 #pragma unroll
-          for (int k = 0; k < FAST_EPT; ++k) z[k] = (lane + 32 * k < niter) ? __ldg(&a.ztab[bo[k]]) : (T)0;
+          for (int k = 0; k < FAST_EPT; ++k) z[k] = live(k) ? __ldg(&a.ztab[bo[k]]) : (T)0;
         }
       } else {
 #pragma unroll
@@ -408,12 +411,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
       // ---- split-chain moments: warp w owns split chain w -------------------------------------------
       double s = 0.0;
 #pragma unroll
-      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) s += (double)z[k];
+      for (int k = 0; k < FAST_EPT; ++k) if (live(k)) s += (double)z[k];
       s = warp_sum(s);
       const T m = (T)(s / (double)niter);
       double q = 0.0;
 #pragma unroll
-      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) { const T d = z[k] - m; q = fma((double)d, (double)d, q); }
+      for (int k = 0; k < FAST_EPT; ++k) if (live(k)) { const T d = z[k] - m; q = fma((double)d, (double)d, q); }
       q = warp_sum(q);
       __syncthreads();  // all resolve loops are done with K / CNT; cmean / cvar free
       if (lane == 0) { cmean[w] = m; cvar[w] = (T)(q / (double)(niter - 1)); }
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
 #pragma unroll
         for (int k = 0; k < FAST_EPT; ++k) {
           const int t = lane + 32 * k;
-          row[t + (t >> 4)] = t < niter ? (double)(T)(z[k] - m) : 0.0;
+          row[t + (t >> 4)] = live(k) ? (double)(T)(z[k] - m) : 0.0;
         }
         for (int t = FAST_MAXITER + lane; t < FAST_TMAX; t += 32) row[t + (t >> 4)] = 0.0;
       }
