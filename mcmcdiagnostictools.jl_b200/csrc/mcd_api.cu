@@ -540,7 +540,9 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
     kern<<<grid, FAST_THREADS, smem, ctx->stream>>>(a);
   } else {
     const size_t smem = fast_smem_bytes<T>(pg.maxlag) + FASTGEN_EXTRA_SMEM + (size_t)ctx->fast_pad_smem;
-    auto kern = ga.mcse_mode == 3 ? fastgen_kernel<T, true> : fastgen_kernel<T, false>;
+    const bool lng = g.niter > 32 * (FAST_EPT - 1);
+    auto kern = ga.mcse_mode == 3 ? (lng ? fastgen_kernel<T, true, true> : fastgen_kernel<T, true, false>)
+                                  : (lng ? fastgen_kernel<T, false, true> : fastgen_kernel<T, false, false>);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(ga);
   }
@@ -623,7 +625,7 @@ static int run_fast_summary(mcd_ctx* ctx, const T* dx, long long params, const S
   a.redo_count = ctx->d_redo; a.redo_list = ctx->d_redo + 1;
   CU(cudaMemsetAsync(ctx->d_redo, 0, sizeof(int), ctx->stream));
   const size_t smem = fast_smem_bytes<T>(a.maxlag) + FASTGEN_EXTRA_SMEM + (size_t)ctx->fast_pad_smem;
-  auto kern = fastgen_kernel<T, false>;
+  auto kern = g.niter > 32 * (FAST_EPT - 1) ? fastgen_kernel<T, false, true> : fastgen_kernel<T, false, false>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)params, FAST_THREADS, smem, ctx->stream>>>(a);
   ctx->launches++;

@@ -69,7 +69,8 @@ template <typename T> struct FastGenArgs {
 
 // QRULE = the program ends with the MCSE order-statistic rule (mcse_mode 3): only that instance carries the
 // window of sorted values and the Beta inverse, so the other programs do not pay for them.
-template <typename T, bool QRULE>
+// LONG: as in mcd_fast.cuh (split chains longer than 480 draws: 15 of the 16 slots are always occupied).
+template <typename T, bool QRULE, bool LONG>
 __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenArgs<T> a) {
   using Key = typename Traits<T>::Key;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int niter = a.niter;
+  auto live = [&](int k) -> bool { return LONG ? (k < FAST_EPT - 1 || lane + 32 * (FAST_EPT - 1) < niter) : (lane + 32 * k < niter); };
   if (tid == 0) { Khi[FAST_SENT] = 0xffffffffu; Khi[FAST_SENT + 1] = 0; }   // [SENT + 1]: work-list length
 
   for (long long param = blockIdx.x; param < a.params; param += gridDim.x) {
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
 #pragma unroll
     for (int k = 0; k < FAST_EPT; ++k) {
       const int t = lane + 32 * k;
-      x[k] = t < niter ? __ldg(&src[t]) : (T)0;
+      x[k] = live(k) ? __ldg(&src[t]) : (T)0;
     }
     bool redo = false;
     T vmin = (T)0, vmax = (T)0;
@@ -121,11 +123,11 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       };
       double sx = 0.0;
 #pragma unroll
-      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) sx += (double)x[k];
+      for (int k = 0; k < FAST_EPT; ++k) if (live(k)) sx += (double)x[k];
       const T mean_all = (T)(block_total(sx) / (double)n);
       double s2 = 0.0, s4 = 0.0;
 #pragma unroll
-      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) {
+      for (int k = 0; k < FAST_EPT; ++k) if (live(k)) {
         const T d = x[k] - mean_all;
         const T pz = d * d;
         s2 += (double)pz;
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           int bad = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            if (lane + 32 * k < niter) {
+            if (live(k)) {
               const T v = x[k];
               bad |= (v != v);
               lmin = v < lmin ? v : lmin;
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           unsigned maxoff = 0, shared_mask = 0;
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            if (lane + 32 * k < niter) {
+            if (live(k)) {
               const unsigned fb = (unsigned)bucket_of<T>(x[k], (double)vmin, (double)scale, FAST_FINE);
               const unsigned sh = (fb & 7u) * 4u;
               const unsigned off = (atomicAdd(&FC[fb >> 3], 1u << sh) >> sh) & 15u;
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           // ---- position: start of the fine bucket, population, own slot; shared buckets scatter ----
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
-            const bool valid = lane + 32 * k < niter;
+            const bool valid = live(k);
             const unsigned fb = bo[k] & 0xffffu, off = bo[k] >> 16;
             const unsigned word = fb >> 3, sh = (fb & 7u) * 4u;
             const unsigned fw = FC[word];
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           if (ncap > 0) {
 #pragma unroll
             for (int k = 0; k < FAST_EPT; ++k) {
-              if (lane + 32 * k < niter && !(shared_mask & (1u << k))) {
+              if (live(k) && !(shared_mask & (1u << k))) {
                 const unsigned m = WANT[bo[k] & 0xfffu];
                 if (m) for (int ci = 0; ci < 6; ++ci) if (m & (1u << ci)) cap[cbase + ci] = (double)x[k];
               }
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
 #pragma unroll
             for (int k = 0; k < FAST_EPT; ++k) {
               const unsigned rel = (bo[k] & 0xfffu) - (unsigned)wlo;
-              if (lane + 32 * k < niter && !(shared_mask & (1u << k)) && rel < (unsigned)FASTGEN_WIN) WIN[rel] = (double)x[k];
+              if (live(k) && !(shared_mask & (1u << k)) && rel < (unsigned)FASTGEN_WIN) WIN[rel] = (double)x[k];
             }
           }
 #pragma unroll
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
             bo[k] = (shared_mask & (1u << k)) ? (unsigned)RES[k * FAST_THREADS + tid] : (bo[k] & 0xfffu);
           if (first_is_rankz) {
 #pragma unroll
-            for (int k = 0; k < FAST_EPT; ++k) z[k] = (lane + 32 * k < niter) ? __ldg(&a.ztab[bo[k]]) : (T)0;
+            for (int k = 0; k < FAST_EPT; ++k) z[k] = live(k) ? __ldg(&a.ztab[bo[k]]) : (T)0;
           }
         }
         // thresholds from the captured order statistics
@@ -437,12 +439,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       // ---- split-chain moments: warp w owns split chain w -------------------------------------------
       double s = 0.0;
 #pragma unroll
-      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) s += (double)z[k];
+      for (int k = 0; k < FAST_EPT; ++k) if (live(k)) s += (double)z[k];
       s = warp_sum(s);
       const T m = (T)(s / (double)niter);
       double q = 0.0;
 #pragma unroll
-      for (int k = 0; k < FAST_EPT; ++k) if (lane + 32 * k < niter) { const T d = z[k] - m; q = fma((double)d, (double)d, q); }
+      for (int k = 0; k < FAST_EPT; ++k) if (live(k)) { const T d = z[k] - m; q = fma((double)d, (double)d, q); }
       q = warp_sum(q);
       __syncthreads();  // all resolve loops are done with K / CNT; cmean / cvar free
       if (lane == 0) { cmean[w] = m; cvar[w] = (T)(q / (double)(niter - 1)); }
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
 #pragma unroll
         for (int k = 0; k < FAST_EPT; ++k) {
           const int t = lane + 32 * k;
-          row[t + (t >> 4)] = t < niter ? (double)(T)(z[k] - m) : 0.0;
+          row[t + (t >> 4)] = live(k) ? (double)(T)(z[k] - m) : 0.0;
         }
         for (int t = FAST_MAXITER + lane; t < FAST_TMAX; t += 32) row[t + (t >> 4)] = 0.0;
       }
