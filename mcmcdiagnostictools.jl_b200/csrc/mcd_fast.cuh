@@ -136,6 +136,14 @@ __device__ __forceinline__ double warp_reduce8(double (&a)[8]) {
   return d;  // lane l holds total of acc[(l >> 2)]: bit4 -> +4, bit3 -> +2, bit2 -> +1
 }
 
+// 15 consecutive draws of a padded row (index t + (t >> 4)) starting at draw 16 q + 8 E + 1, given
+// base = row + 17 q: every offset is a compile-time constant.
+template <int E>
+__device__ __forceinline__ void fast_window(const double* base, double (&win)[15]) {
+#pragma unroll
+  for (int i = 0; i < 15; ++i) win[i] = base[(8 * E + 1 + i) + ((8 * E + 1 + i) >> 4)];
+}
+
 // exact (less, eq) of an element inside its bucket on the full key; returns less | eq << 16.
 // Kept out of line: it runs only for elements whose hi word collides with a bucket-mate's.
 template <bool TWO>
@@ -454,8 +462,16 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
           double own[8], win[15];
 #pragma unroll
           for (int i = 0; i < 8; ++i) own[i] = row[t0 + i + lane];      // (t0+i)>>4 == lane
+          // window draws t0 + k0 .. t0 + k0 + 14 with k0 = 8 b + 1: in units of 8 draws the window starts at
+          // c = b + h, and with the parity of c known every padded index is the lane's base + a constant
+          const int c = (k0 >> 3) + h;
+          if (c <= 8) {   // the whole window lies inside the zero-filled row: no bound checks
+            const double* base = row + 17 * (lane + (c >> 1));
+            if (c & 1) fast_window<1>(base, win); else fast_window<0>(base, win);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 15; ++i) { const int t = t0 + k0 + i; win[i] = t < FAST_TMAX ? row[t + (t >> 4)] : 0.0; }
+            for (int i = 0; i < 15; ++i) { const int t = t0 + k0 + i; win[i] = t < FAST_TMAX ? row[t + (t >> 4)] : 0.0; }
+          }
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
 #pragma unroll
