@@ -48,7 +48,7 @@ constexpr int FAST_SENT = FAST_NMAX;      // index of the sentinel key (0xffffff
 
 // shared-memory layout (bytes):
 //   [ FC  : FAST_WORDS u32 ][ WP : FAST_WORDS u16 ]     <- aliased by ZC[8][FAST_ROW] doubles
-//   [ Khi : FAST_NMAX + 32 u32 ][ Klo : FAST_NMAX u32 ]
+//   [ KV : FAST_NMAX values of T (the region is sized for two u32 planes: FAST_NMAX + 32 and FAST_NMAX words) ]
 //   [ small arrays ]
 constexpr int FAST_OFF_WP = FAST_WORDS * 4;
 constexpr int FAST_OFF_KHI = FAST_OFF_WP + FAST_WORDS * 2;
@@ -170,8 +170,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
   const int n = FAST_NCH * a.niter;
   unsigned* FC = reinterpret_cast<unsigned*>(smem);
   unsigned short* WP = reinterpret_cast<unsigned short*>(smem + FAST_OFF_WP);
-  unsigned* Khi = reinterpret_cast<unsigned*>(smem + FAST_OFF_KHI);
-  unsigned* Klo = reinterpret_cast<unsigned*>(smem + FAST_OFF_KLO);
+  T* KV = reinterpret_cast<T*>(smem + FAST_OFF_KHI);   // values of shared-bucket members at their sorted slots
   double* ZC = reinterpret_cast<double*>(smem);
   unsigned char* small = smem + FAST_OFF_SMALL;
   T* cmean = reinterpret_cast<T*>(small);                  // [8]
@@ -180,13 +179,14 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
   double* wred = part + 64;                                // [2][8]
   double* thr = wred + 16;                                 // [4]
   int* iflag = reinterpret_cast<int*>(thr + 4);            // [8] warp totals / flags
-  int* woffx = iflag + 8;                                  // [8] exclusive warp offsets
+  int* woffx = iflag + 8;                                  // [8] [0] = length of the work list
   T* gamma = reinterpret_cast<T*>(woffx + 8);              // [maxlag + 9]
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int niter = a.niter;
   auto live = [&](int k) -> bool { return LONG ? (k < FAST_EPT - 1 || lane + 32 * (FAST_EPT - 1) < niter) : (lane + 32 * k < niter); };
-  if (tid == 0) { Khi[FAST_SENT] = 0xffffffffu; Khi[FAST_SENT + 1] = 0; }   // sentinel (unused by the list resolve); list length
+  unsigned* listlen = reinterpret_cast<unsigned*>(woffx);
+  if (tid == 0) *listlen = 0;
 
   for (long long param = blockIdx.x; param < a.params; param += gridDim.x) {
     const T* __restrict__ src = a.x + param * (long long)n + w * niter;
@@ -330,8 +330,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
             const unsigned st = (unsigned)WP[word] + __shfl_sync(0xffffffffu, woff, (int)(word >> 10)) + nibsum(fw & ((1u << sh) - 1u));
             const unsigned c = valid ? ((fw >> sh) & 15u) : 0u;
             if (c >= 2u) {
-              Khi[st + off] = key_hi(x[k]);
-              if (FastKeys<T>::TWO) Klo[st + off] = key_lo(x[k]);
+              KV[st + off] = x[k];
             }
             bo[k] = st | (c << 12) | (off << 16);   // st <= 4095
             shared_mask |= (c >= 2u ? 1u : 0u) << k;
@@ -354,7 +353,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
               if (lane >= o) incl += t;
             }
             unsigned base = 0;
-            if (lane == 31) base = atomicAdd(&Khi[FAST_SENT + 1], incl);
+            if (lane == 31) base = atomicAdd(listlen, incl);
             unsigned q = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
             const unsigned slot0 = (unsigned)tid << 20;
             if (mine) {
@@ -365,35 +364,25 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
           }
           __syncthreads();
           {
-            const unsigned listn = Khi[FAST_SENT + 1];
+            const unsigned listn = *listlen;
             for (unsigned q = tid; q < listn; q += FAST_THREADS) {
               const unsigned it = WL[q];
               const unsigned st = it & 0xfffu, c = (it >> 12) & 15u, off = (it >> 16) & 15u;
-              const unsigned vhi = Khi[st + off];
-              const unsigned vlo = FastKeys<T>::TWO ? Klo[st + off] : 0u;
+              // exact counts against the bucket mates on the values themselves (== ties -0.0 with 0.0, as tiedrank does)
+              const T v = KV[st + off];
               unsigned less = 0, eq = 0;
-              for (unsigned j = st; j < st + c; ++j) {
-                const unsigned yhi = Khi[j];
-                if (yhi < vhi) ++less;
-                else if (yhi == vhi) {
-                  if constexpr (FastKeys<T>::TWO) { const unsigned ylo = Klo[j]; less += ylo < vlo; eq += ylo == vlo; }
-                  else ++eq;
-                }
-              }
+              for (unsigned j = st; j < st + c; ++j) { const T y = KV[j]; less += y < v; eq += y == v; }
               const int lo = (int)(st + less), hi = lo + (int)eq;
-              if (capture && ((lo <= mA && mA < hi) || (lo <= mB && mB < hi))) {
-                double v;
-                if constexpr (FastKeys<T>::TWO) v = key_value(((unsigned long long)vhi << 32) | vlo);
-                else v = (double)key_value(vhi);
-                if (lo <= mA && mA < hi) thr[0] = v;
-                if (lo <= mB && mB < hi) thr[1] = v;
+              if (capture) {
+                if (lo <= mA && mA < hi) thr[0] = (double)v;
+                if (lo <= mB && mB < hi) thr[1] = (double)v;
               }
               const unsigned zi = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
               RES[it >> 20] = (unsigned short)((zi >> 1) + ((zi & 1u) ? (unsigned)n : 0u));   // split z table
             }
           }
           __syncthreads();
-          if (tid == 0) Khi[FAST_SENT + 1] = 0;
+          if (tid == 0) *listlen = 0;
           if (capture) {
 #pragma unroll
             for (int k = 0; k < FAST_EPT; ++k) {

@@ -77,8 +77,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
   const int n = FAST_NCH * a.niter;
   unsigned* FC = reinterpret_cast<unsigned*>(smem);
   unsigned short* WP = reinterpret_cast<unsigned short*>(smem + FAST_OFF_WP);
-  unsigned* Khi = reinterpret_cast<unsigned*>(smem + FAST_OFF_KHI);
-  unsigned* Klo = reinterpret_cast<unsigned*>(smem + FAST_OFF_KLO);
+  T* KV = reinterpret_cast<T*>(smem + FAST_OFF_KHI);   // values of shared-bucket members at their sorted slots
   double* ZC = reinterpret_cast<double*>(smem);
   double* WIN = reinterpret_cast<double*>(smem + FAST_NCH * FAST_ROW * 8);   // [FASTGEN_WIN] sorted values, behind ZC
   unsigned char* small = smem + FAST_OFF_SMALL;
@@ -91,13 +90,14 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
   double* res = thrv + 4;                                  // [12] ess[6], rhat[6] per result slot
   double* side = res + 12;                                 // [4] mean, std, mean(proxy), mean(proxy^2) over the slab
   int* iflag = reinterpret_cast<int*>(side + 4);           // [8] warp totals / flags
-  int* woffx = iflag + 8;                                  // [8] exclusive warp offsets
+  int* woffx = iflag + 8;                                  // [8] [0] = length of the work list
   T* gamma = reinterpret_cast<T*>(woffx + 8);              // [maxlag + 9]
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int niter = a.niter;
   auto live = [&](int k) -> bool { return LONG ? (k < FAST_EPT - 1 || lane + 32 * (FAST_EPT - 1) < niter) : (lane + 32 * k < niter); };
-  if (tid == 0) { Khi[FAST_SENT] = 0xffffffffu; Khi[FAST_SENT + 1] = 0; }   // [SENT + 1]: work-list length
+  unsigned* listlen = reinterpret_cast<unsigned*>(woffx);
+  if (tid == 0) *listlen = 0;
 
   for (long long param = blockIdx.x; param < a.params; param += gridDim.x) {
     const T* __restrict__ src = a.x + param * (long long)n + w * niter;
@@ -277,8 +277,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
             const unsigned st = (unsigned)WP[word] + __shfl_sync(0xffffffffu, woff, (int)(word >> 10)) + nibsum(fw & ((1u << sh) - 1u));
             const unsigned c = valid ? ((fw >> sh) & 15u) : 0u;
             if (c >= 2u) {
-              Khi[st + off] = key_hi(x[k]);
-              if (FastKeys<T>::TWO) Klo[st + off] = key_lo(x[k]);
+              KV[st + off] = x[k];
             }
             bo[k] = st | (c << 12) | (off << 16);   // st <= 4095
             shared_mask |= (c >= 2u ? 1u : 0u) << k;
@@ -318,7 +317,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
               if (lane >= o) incl += t;
             }
             unsigned base = 0;
-            if (lane == 31) base = atomicAdd(&Khi[FAST_SENT + 1], incl);
+            if (lane == 31) base = atomicAdd(listlen, incl);
             unsigned q = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
             const unsigned slot0 = (unsigned)tid << 20;
             if (mine) {
@@ -329,44 +328,29 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
           }
           __syncthreads();
           {
-            const unsigned listn = Khi[FAST_SENT + 1];
+            const unsigned listn = *listlen;
             for (unsigned q = tid; q < listn; q += FAST_THREADS) {
               const unsigned it = WL[q];
               const unsigned st = it & 0xfffu, c = (it >> 12) & 15u, off = (it >> 16) & 15u;
-              const unsigned vhi = Khi[st + off];
-              const unsigned vlo = FastKeys<T>::TWO ? Klo[st + off] : 0u;
+              // exact counts against the bucket mates on the values themselves (== ties -0.0 with 0.0, as tiedrank does)
+              const T v = KV[st + off];
               unsigned less = 0, eq = 0;
-              for (unsigned j = st; j < st + c; ++j) {
-                const unsigned yhi = Khi[j];
-                if (yhi < vhi) ++less;
-                else if (yhi == vhi) {
-                  if constexpr (FastKeys<T>::TWO) { const unsigned ylo = Klo[j]; less += ylo < vlo; eq += ylo == vlo; }
-                  else ++eq;
-                }
-              }
+              for (unsigned j = st; j < st + c; ++j) { const T y = KV[j]; less += y < v; eq += y == v; }
               const int lo = (int)(st + less), hi = lo + (int)eq;
               if (ncap > 0) {
                 unsigned m = 0;
                 for (int pos = lo; pos < hi; ++pos) m |= WANT[pos];
-                if (m) {
-                  double v;
-                  if constexpr (FastKeys<T>::TWO) v = key_value(((unsigned long long)vhi << 32) | vlo);
-                  else v = (double)key_value(vhi);
-                  for (int ci = 0; ci < 6; ++ci) if (m & (1u << ci)) cap[cbase + ci] = v;
-                }
+                if (m) for (int ci = 0; ci < 6; ++ci) if (m & (1u << ci)) cap[cbase + ci] = (double)v;
               }
               if (fill_win) {
-                double v;
-                if constexpr (FastKeys<T>::TWO) v = key_value(((unsigned long long)vhi << 32) | vlo);
-                else v = (double)key_value(vhi);
-                for (int pos = lo; pos < hi; ++pos) if ((unsigned)(pos - wlo) < (unsigned)FASTGEN_WIN) WIN[pos - wlo] = v;
+                for (int pos = lo; pos < hi; ++pos) if ((unsigned)(pos - wlo) < (unsigned)FASTGEN_WIN) WIN[pos - wlo] = (double)v;
               }
               const unsigned zi = (unsigned)(lo + hi - 1);   // r2 - 2 = 2*lo + eq - 1
               RES[it >> 20] = (unsigned short)((zi >> 1) + ((zi & 1u) ? (unsigned)n : 0u));   // split z table
             }
           }
           __syncthreads();
-          if (tid == 0) Khi[FAST_SENT + 1] = 0;
+          if (tid == 0) *listlen = 0;
           if (ncap > 0) {
 #pragma unroll
             for (int k = 0; k < FAST_EPT; ++k) {
