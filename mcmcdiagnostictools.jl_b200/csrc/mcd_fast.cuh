@@ -62,7 +62,7 @@ template <typename T> static inline size_t fast_smem_bytes(int maxlag) {
 // sum of the eight 4-bit fields of w (each <= 15)
 __device__ __forceinline__ unsigned nibsum(unsigned w) {
   const unsigned t = (w & 0x0f0f0f0fu) + ((w >> 4) & 0x0f0f0f0fu);
-  return (t * 0x01010101u) >> 24;
+  return __dp4a(t, 0x01010101u, 0u);   // sum of the four bytes
 }
 // hi / lo words of the order-preserving key of a non-NaN value (see order_key_nonan)
 __device__ __forceinline__ unsigned key_hi(double v) {
@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int niter = a.niter;
-  auto live = [&](int k) -> bool { return LONG ? (k < FAST_EPT - 1 || lane + 32 * (FAST_EPT - 1) < niter) : (lane + 32 * k < niter); };
+  const bool last_live = lane + 32 * (FAST_EPT - 1) < niter;
+  auto live = [&](int k) -> bool { return LONG ? (k < FAST_EPT - 1 || last_live) : (lane + 32 * k < niter); };
   unsigned* listlen = reinterpret_cast<unsigned*>(woffx);
   if (tid == 0) *listlen = 0;
 
