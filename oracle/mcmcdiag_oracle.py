@@ -21,7 +21,9 @@ bulk ESS (:329-335), slice consistency (:167-204), direct ~ FFT and identical R-
 methods (:228-230), direct/FFT ~ StatsBase.autocov(demean=true) (:259-266), rank-normalised
 mean/std (test/utils.jl:98-107), fold identity (:109-123), the nested identity
 sqrt(rhat^2 + 1/n) (test/rhat_nested.jl:132-146), rank == max(bulk, tail) (:148-155), and an
-independent rank check against scipy.stats.rankdata(method="average").
+independent rank check against scipy.stats.rankdata(method="average").  For the callers added from
+SURVEY §8(f): the literal golden values of test/bfmi.jl (0.6 by hand, ArviZ's 0.2406937229) and the
+classical Cramer-von Mises critical values for `pcramer` (src/heideldiag.jl:60-71).
 
 Third-party arithmetic that lives outside /root/reference (versions bounded by
 Project.toml:23-36 only) is restated from its published algorithm:
