@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmcmcdiag_b200.so")
+LIB_PATH = os.environ.get("MCMCDIAG_B200_LIB") or os.path.join(HERE, "libmcmcdiag_b200.so")   # override: A/B builds
 
 MCD_OK, MCD_EINVAL, MCD_ECUDA, MCD_ENOMEM, MCD_EUNSUPPORTED, MCD_ENAN = 0, -1, -2, -3, -4, -5
 MCD_F32, MCD_F64 = 0, 1

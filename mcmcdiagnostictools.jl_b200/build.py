@@ -11,7 +11,7 @@ LIB = os.path.join(HERE, "libmcmcdiag_b200.so")
 SOURCES = ["mcd_api.cu"]
 HEADERS = ["mcd_common.cuh", "mcd_slab.cuh", "mcd_fast.cuh", "mcd_fastgen.cuh", "mcd_large.cuh"]
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-split-compile=0",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 

@@ -254,7 +254,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
         }
         const bool is_const = !(vmax > vmin);
         const T range = vmax - vmin;
-        const T scale = (T)FAST_FINE / range;
+        // slightly less than FINE / range: the largest value lands inside the last bucket, the smallest in bucket 0,
+        // so the map needs no clamping (still monotone)
+        const T scale = (T)((double)FAST_FINE * (1.0 - 1.0 / 1048576.0)) / range;
         if (!is_const && (!(range < (T)CUDART_INF) || !(scale > (T)0) || !(scale < (T)CUDART_INF))) { redo = true; break; }
         if (is_const) {
           // every value ties: rank (n+1)/2
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
 #pragma unroll
           for (int k = 0; k < FAST_EPT; ++k) {
             if (live(k)) {
-              const unsigned fb = (unsigned)bucket_of<T>(x[k], (double)vmin, (double)scale, FAST_FINE);
+              const unsigned fb = (unsigned)(int)((x[k] - vmin) * scale);
               const unsigned sh = (fb & 7u) * 4u;
               const unsigned off = (atomicAdd(&FC[fb >> 3], 1u << sh) >> sh) & 15u;
               maxoff = off > maxoff ? off : maxoff;
