@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
   unsigned* FC = reinterpret_cast<unsigned*>(smem);
   unsigned short* WP = reinterpret_cast<unsigned short*>(smem + FAST_OFF_WP);
   T* KV = reinterpret_cast<T*>(smem + FAST_OFF_KHI);   // values of shared-bucket members at their sorted slots
+  unsigned* WC = reinterpret_cast<unsigned*>(smem + FAST_OFF_KHI);   // per-word populations as bytes (count + scan only; KV is written later)
   double* ZC = reinterpret_cast<double*>(smem);
   unsigned char* small = smem + FAST_OFF_SMALL;
   T* cmean = reinterpret_cast<T*>(small);                  // [8]
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
         __syncthreads();  // previous users of the big region (ZC / K / CNT) are done
         // clear the packed counters now: the barrier of the min / max exchange (pass 0) covers it
         for (int i = tid; i < FAST_WORDS / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(FC)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < FAST_WORDS / 16; i += FAST_THREADS) reinterpret_cast<uint4*>(WC)[i] = make_uint4(0, 0, 0, 0);
         if (pass == 1) __syncthreads();
         if (pass == 0) {
           T lmin = (T)CUDART_INF, lmax = -(T)CUDART_INF;
@@ -274,40 +276,56 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
               const unsigned fb = (unsigned)(int)((x[k] - vmin) * scale);
               const unsigned sh = (fb & 7u) * 4u;
               const unsigned off = (atomicAdd(&FC[fb >> 3], 1u << sh) >> sh) & 15u;
+              atomicAdd(&WC[fb >> 5], 1u << ((fb >> 3) & 3u) * 8u);   // population of the counter word, one byte per word
               maxoff = off > maxoff ? off : maxoff;
               bo[k] = fb | (off << 16);
             } else bo[k] = 0;
           }
           // a counter that reaches 16 spills into its neighbour: the value that did it saw 15
           if (__syncthreads_or(maxoff >= 15u)) { redo = true; break; }
-          // ---- scan: WP[word] = #values in earlier words of this warp's 1024-word range ---------
+          // ---- scan: WP[word] = #values in earlier words of this warp's 1024-word range.  The byte
+          // populations of 4 words sit in one u32; a lane owns two runs of 16 words (conflict-free 128-bit
+          // loads) and one warp scan carries both runs as two 16-bit partial sums -----------------------------
           {
-            unsigned carry = 0;
-#pragma unroll 1
-            for (int it = 0; it < 4; ++it) {
-              const int wbase = w * 1024 + it * 256 + 4 * lane;
-              const uint4 c4 = *reinterpret_cast<const uint4*>(FC + wbase);
-              const uint4 d4 = *reinterpret_cast<const uint4*>(FC + wbase + 128);
-              const unsigned c0 = nibsum(c4.x), c1 = nibsum(c4.y), c2 = nibsum(c4.z), c3 = nibsum(c4.w);
-              const unsigned d0 = nibsum(d4.x), d1 = nibsum(d4.y), d2 = nibsum(d4.z), d3 = nibsum(d4.w);
-              const unsigned tot = (c0 + c1 + c2 + c3) | ((d0 + d1 + d2 + d3) << 16);
-              unsigned incl = tot;
+            const uint4* wc4 = reinterpret_cast<const uint4*>(WC + w * (FAST_WORDS / 32));
+            const uint4 ca = wc4[lane], cb = wc4[32 + lane];
+            const unsigned C[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+            unsigned lo[8], pr[8], tt[8];
 #pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-              }
-              const unsigned all = __shfl_sync(0xffffffffu, incl, 31);
-              const unsigned excl = incl - tot;
-              const unsigned s0 = carry + (excl & 0xffffu);
-              const unsigned s1 = carry + (all & 0xffffu) + (excl >> 16);
-              uint2 pc, pd;
-              pc.x = s0 | ((s0 + c0) << 16); pc.y = (s0 + c0 + c1) | ((s0 + c0 + c1 + c2) << 16);
-              pd.x = s1 | ((s1 + d0) << 16); pd.y = (s1 + d0 + d1) | ((s1 + d0 + d1 + d2) << 16);
-              *reinterpret_cast<uint2*>(WP + wbase) = pc;
-              *reinterpret_cast<uint2*>(WP + wbase + 128) = pd;
-              carry += (all & 0xffffu) + (all >> 16);
+            for (int i = 0; i < 8; ++i) {
+              lo[i] = C[i] & 0x00ff00ffu;                        // (b2, b0) in 16-bit lanes
+              pr[i] = lo[i] + ((C[i] >> 8) & 0x00ff00ffu);       // (b2 + b3, b0 + b1)
+              tt[i] = (pr[i] & 0xffffu) + (pr[i] >> 16);         // population of the 4 words
             }
+            const unsigned totA = tt[0] + tt[1] + tt[2] + tt[3], totB = tt[4] + tt[5] + tt[6] + tt[7];
+            const unsigned tot = totA | (totB << 16);
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            const unsigned all = __shfl_sync(0xffffffffu, incl, 31);
+            const unsigned excl = incl - tot;
+            unsigned out[16];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              unsigned base = hf == 0 ? (excl & 0xffffu) : (all & 0xffffu) + (excl >> 16);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = 4 * hf + i;
+                const unsigned B = base * 0x00010001u;                                       // (base, base)
+                out[2 * j] = B + (lo[j] << 16);                                              // words 4j, 4j+1: base, base + b0
+                out[2 * j + 1] = B + (pr[j] & 0xffffu) * 0x00010001u + (lo[j] & 0xffff0000u);  // base + b0 + b1, ... + b2
+                base += tt[j];
+              }
+            }
+            uint4* wp4 = reinterpret_cast<uint4*>(WP + w * (FAST_WORDS / 8)) + 2 * lane;
+            wp4[0] = make_uint4(out[0], out[1], out[2], out[3]);
+            wp4[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            wp4[FAST_WORDS / 128] = make_uint4(out[8], out[9], out[10], out[11]);
+            wp4[FAST_WORDS / 128 + 1] = make_uint4(out[12], out[13], out[14], out[15]);
+            const unsigned carry = (all & 0xffffu) + (all >> 16);
             if (lane == 0) iflag[w] = (int)carry;
             __syncthreads();
           }
