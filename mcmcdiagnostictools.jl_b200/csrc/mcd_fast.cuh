@@ -452,15 +452,19 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
       __syncthreads();
       SplitGeom g8;
       g8.niter = niter; g8.nch = FAST_NCH;
-      T W, var_plus;
+      // W and var_plus feed Geyer's loop on every thread; R-hat itself is only thread 0's business
+      T W = (T)0, var_plus = (T)0;
       within_between<T>(cmean, cvar, g8, W, var_plus);
-      const double rh = (double)sqrt(var_plus / W);
-      if (pass == 0) rhat_bulk = rh; else rhat_tail = rh;
+      if (tid == 0) {
+        const double rh = (double)sqrt(var_plus / W);
+        if (pass == 0) rhat_bulk = rh; else rhat_tail = rh;
+      }
       if (!do_ess) continue;
 
       // ---- direct autocovariance, lazily, Geyer truncation (ess_rhat.jl:553-594) -----------------
       const int maxlag = a.maxlag;
       int have = 0;
+      const T inv_var_plus = (T)1 / var_plus;
       auto batch = [&](int k0) {
         const double* row = ZC + w * FAST_ROW;
         double acc[8];
@@ -496,14 +500,14 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
             double sum = 0.0;
 #pragma unroll
             for (int i = 0; i < FAST_NCH; ++i) sum += part[i * 8 + tid];
-            gamma[k] = (T)(sum / (double)FAST_NCH) / (T)niter;
+            const T gk = (T)(sum / (double)FAST_NCH) / (T)niter;
+            gamma[k] = (T)1 - inv_var_plus * (W - gk);   // rho_k (ess_rhat.jl:556,566-567): stored instead of gamma_k
           }
         }
         __syncthreads();
       };
       auto ensure = [&](int k) { while (have < k) { batch(have + 1); have += 8; } };
-      const T inv_var_plus = (T)1 / var_plus;
-      auto rho = [&](int k) -> T { return (T)1 - inv_var_plus * (W - gamma[k]); };
+      auto rho = [&](int k) -> T { return gamma[k]; };
       ensure(1);
       T rho_odd = rho(1), rho_even = (T)1;
       T p_t = rho_even + rho_odd, sum_p = p_t;
@@ -519,10 +523,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
         k += 2;
       }
       if (maxlag > 1) { ensure(k); rho_even = rho(k); } else rho_even = (T)0;
-      const T tau = jl_max<T>((T)0, (T)2 * sum_p + jl_max<T>((T)0, rho_even) - (T)1);
-      T e = jl_min<T>((T)1 / tau, a.rel_ess_max);
-      if (!a.relative) e *= (T)(niter * FAST_NCH);
-      ess = (double)e;
+      if (tid == 0) {
+        const T tau = jl_max<T>((T)0, (T)2 * sum_p + jl_max<T>((T)0, rho_even) - (T)1);
+        T e = jl_min<T>((T)1 / tau, a.rel_ess_max);
+        if (!a.relative) e *= (T)(niter * FAST_NCH);
+        ess = (double)e;
+      }
     }
 
     if (redo) {
