@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       // ---- direct autocovariance, lazily, Geyer truncation (ess_rhat.jl:553-594) -----------------
       const int maxlag = a.maxlag;
       int have = 0;
+      const T inv_var_plus = (T)1 / var_plus;
       auto batch = [&](int k0) {
         const double* row = ZC + w * FAST_ROW;
         double acc[8];
@@ -481,14 +482,14 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
             double sum = 0.0;
 #pragma unroll
             for (int i = 0; i < FAST_NCH; ++i) sum += part[i * 8 + tid];
-            gamma[k] = (T)(sum / (double)FAST_NCH) / (T)niter;
+            const T gk = (T)(sum / (double)FAST_NCH) / (T)niter;
+            gamma[k] = (T)1 - inv_var_plus * (W - gk);   // rho_k (ess_rhat.jl:556,566-567): stored instead of gamma_k
           }
         }
         __syncthreads();
       };
       auto ensure = [&](int k) { while (have < k) { batch(have + 1); have += 8; } };
-      const T inv_var_plus = (T)1 / var_plus;
-      auto rho = [&](int k) -> T { return (T)1 - inv_var_plus * (W - gamma[k]); };
+      auto rho = [&](int k) -> T { return gamma[k]; };
       ensure(1);
       T rho_odd = rho(1), rho_even = (T)1;
       T p_t = rho_even + rho_odd, sum_p = p_t;
