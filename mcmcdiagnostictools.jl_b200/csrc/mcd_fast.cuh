@@ -452,9 +452,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fast_kernel(const FastArgs<T>
       __syncthreads();
       SplitGeom g8;
       g8.niter = niter; g8.nch = FAST_NCH;
-      // W and var_plus feed Geyer's loop on every thread; R-hat itself is only thread 0's business
-      T W = (T)0, var_plus = (T)0;
-      within_between<T>(cmean, cvar, g8, W, var_plus);
+      // W and var_plus are used by the threads that form rho_k (tid < 8) and by thread 0 (R-hat): warp 0 only
+      T W = (T)0, var_plus = (T)1;
+      if (w == 0) within_between<T>(cmean, cvar, g8, W, var_plus);
       if (tid == 0) {
         const double rh = (double)sqrt(var_plus / W);
         if (pass == 0) rhat_bulk = rh; else rhat_tail = rh;

@@ -446,8 +446,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
       __syncthreads();
       SplitGeom g8;
       g8.niter = niter; g8.nch = FAST_NCH;
-      T W, var_plus;
-      within_between<T>(cmean, cvar, g8, W, var_plus);
+      // W and var_plus are used by the threads that form rho_k (tid < 8) and by thread 0 (R-hat): warp 0 only
+      T W = (T)0, var_plus = (T)1;
+      if (w == 0) within_between<T>(cmean, cvar, g8, W, var_plus);
       if (tid == 0) { res[6 + slot] = (double)sqrt(var_plus / W); res[slot] = (double)Traits<T>::nan(); }
       if (!do_ess) continue;
 
@@ -505,10 +506,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) fastgen_kernel(const FastGenA
         k += 2;
       }
       if (maxlag > 1) { ensure(k); rho_even = rho(k); } else rho_even = (T)0;
-      const T tau = jl_max<T>((T)0, (T)2 * sum_p + jl_max<T>((T)0, rho_even) - (T)1);
-      T e = jl_min<T>((T)1 / tau, a.rel_ess_max);
-      if (!a.relative) e *= (T)(niter * FAST_NCH);
-      if (tid == 0) res[slot] = (double)e;
+      if (tid == 0) {
+        const T tau = jl_max<T>((T)0, (T)2 * sum_p + jl_max<T>((T)0, rho_even) - (T)1);
+        T e = jl_min<T>((T)1 / tau, a.rel_ess_max);
+        if (!a.relative) e *= (T)(niter * FAST_NCH);
+        res[slot] = (double)e;
+      }
       }   // reductions
       if (redo) break;
     }
