@@ -398,3 +398,30 @@ def test_gelmandiag_oracle_behaviour():
         o.gelmandiag(x[:, :1, :])
     y = rng.standard_normal((500, 4, 2)); y[:, 0, 0] += 3.0
     assert o.gelmandiag(y)["psrf"][0] > 1.2 and abs(o.gelmandiag(y)["psrf"][1] - 1) < 0.05
+
+
+def test_host_pcramer_matches_oracle():
+    """The host mirror's vectorised Cramer-von Mises series (api._pcramer) equals the oracle's scalar one."""
+    from oracle import mcmcdiag_oracle as o
+    import mcmcdiag_b200 as m
+    q = np.array([0.01, 0.05, 0.2, 0.34730, 0.46136, 0.74346, 1.5, 3.0])
+    got = m.api._pcramer(q)
+    want = np.array([o.pcramer(v) for v in q])
+    assert np.allclose(got, want, rtol=1e-14, atol=0)
+
+
+def test_callers_argument_errors_need_no_gpu():
+    """Argument validation of the host wrappers happens before any device call (test/gewekediag.jl:10-18)."""
+    import mcmcdiag_b200 as m
+    x = np.random.default_rng(0).standard_normal(100)
+    for v in (-0.3, 0, 1, 1.2):
+        with pytest.raises(m.ArgumentError):
+            m.gewekediag(x, first=v)
+    with pytest.raises(m.ArgumentError):
+        m.gewekediag(x, first=0.6, last=0.5)
+    with pytest.raises(RuntimeError):
+        m.gelmandiag(np.zeros((10, 1, 2)))
+    with pytest.raises(m.ArgumentError):
+        m.summary(np.zeros((100, 4, 2)), fields=("bogus",))
+    with pytest.raises(m.ArgumentError):
+        m.bfmi(np.zeros((4, 4, 4)))
