@@ -5,16 +5,17 @@
 // One CTA (8 warps) per parameter, ONE WARP PER SPLIT CHAIN, the slab held in registers:
 //   * global -> registers, coalesced, 16 independent loads in flight per thread (the slab is
 //     read from HBM exactly once and never staged);
-//   * rank-normalisation by counting into 65 536 FINE buckets (monotone linear map) whose
-//     populations live in 4-bit packed counters (8 per word, 32 KB): one shared-memory atomic per
-//     element returns its arrival offset; a nibble-sum scan gives a 16-bit prefix per counter
-//     word; an element's sorted position is prefix + nibble-sum of the lower counters of its
-//     word.  With n <= 4096 values ~90 % of the elements are alone in their bucket and are
-//     ranked in O(1) with no key traffic at all; only members of shared buckets scatter their
-//     order-preserving key (32-bit hi / lo planes) and compare against their few bucket mates
-//     (warp-uniform trip count, inactive lanes read a broadcast sentinel).  A hi-plane tie is
-//     settled exactly on (hi, lo) out of line.  Exact average-tie ranks; z from a table indexed
-//     by the doubled rank;
+//   * rank-normalisation by counting into 65 536 FINE buckets (monotone linear map, scaled so that
+//     no clamping is needed) whose populations live in 4-bit packed counters (8 per word, 32 KB):
+//     one shared-memory atomic per element returns its arrival offset, a second one keeps the
+//     population of the counter word as a byte, so that one warp-shuffle scan over 4 words per
+//     u32 gives a 16-bit prefix per counter word; an element's sorted position is prefix +
+//     nibble-sum of the lower counters of its word.  With n <= 4096 values ~90 % of the elements
+//     are alone in their bucket and are ranked in O(1) (their z-table index is their position);
+//     members of shared buckets store their VALUE at their sorted slot, are compacted into a work
+//     list and resolved by all 256 threads: exact (less, equal) counts against the few bucket mates
+//     by comparing values.  Exact average-tie ranks; z from a table indexed by the doubled rank
+//     (integer ranks first, so untied data keeps half of it hot in L1);
 //   * the median for the fold is captured from the ranks (no selection pass); the folded values
 //     are ranked by the same code (second pass of the loop), so `:rank` costs one HBM read;
 //   * split-chain moments are warp-shuffle reductions on registers;
@@ -24,9 +25,11 @@
 // Slabs that need the general machinery (NaN, infinite range, a fine bucket holding >= 15
 // values, i.e. heavy ties) are appended to a redo list and recomputed by the general slab kernel.
 //
-// History (profiles/README.md): v0 ranked with 8192 coarse buckets and compare rounds for every
-// element (83 k warp-instructions per parameter, issue-bound in the ranking phases: IPC ~3 there,
-// insensitive to the bucket count and to doubling the resident warps).
+// Compile-time specialisation LONG (split chains longer than 480 draws, e.g. the canonical 500): only
+// the last of a thread's 16 slots can be empty, so the validity tests of the other 15 fold away.
+// Work that only a few threads consume (R-hat, rho_k, the ESS finalisation) runs on those threads
+// only: anything repeated by all 8 warps costs 8 x its instruction count.
+// History and measurements: profiles/README.md.
 //
 // Reference citations (/root/reference): utils.jl:13-41,148-193; ess_rhat.jl:362-409,488-624.
 #pragma once
@@ -44,7 +47,6 @@ constexpr int FAST_TMAX = 576;            // the row is zero-filled on [niter, F
 constexpr int FAST_FINE = 65536;          // fine buckets
 constexpr int FAST_WORDS = FAST_FINE / 8; // counter words (8 nibbles each)
 constexpr int FAST_NMAX = FAST_NCH * FAST_MAXITER;  // 4096
-constexpr int FAST_SENT = FAST_NMAX;      // index of the sentinel key (0xffffffff) in Khi
 
 // shared-memory layout (bytes):
 //   [ FC  : FAST_WORDS u32 ][ WP : FAST_WORDS u16 ]     <- aliased by ZC[8][FAST_ROW] doubles
@@ -64,18 +66,6 @@ __device__ __forceinline__ unsigned nibsum(unsigned w) {
   const unsigned t = (w & 0x0f0f0f0fu) + ((w >> 4) & 0x0f0f0f0fu);
   return __dp4a(t, 0x01010101u, 0u);   // sum of the four bytes
 }
-// hi / lo words of the order-preserving key of a non-NaN value (see order_key_nonan)
-__device__ __forceinline__ unsigned key_hi(double v) {
-  const int h = __double2hiint(v + 0.0);
-  return (unsigned)(h ^ ((h >> 31) | (int)0x80000000u));
-}
-__device__ __forceinline__ unsigned key_lo(double v) {
-  const double u = v + 0.0;
-  return (unsigned)(__double2loint(u) ^ (__double2hiint(u) >> 31));
-}
-__device__ __forceinline__ unsigned key_hi(float v) { return order_key_nonan(v); }
-__device__ __forceinline__ unsigned key_lo(float v) { return 0u; }
-
 template <typename T> struct FastArgs {
   const T* x;
   long long params;
@@ -94,10 +84,6 @@ template <typename T> struct FastArgs {
   int* redo_list;
   int* redo_count;
 };
-
-template <typename T> struct FastKeys;
-template <> struct FastKeys<double> { static constexpr bool TWO = true; };
-template <> struct FastKeys<float> { static constexpr bool TWO = false; };
 
 // sum of 8 per-lane accumulators over the warp with 9 double shuffles; lane (l & 7) ... see below:
 // after the call, lanes whose (l >> 2) == q hold the total of acc[q] (q = 0..7).
@@ -142,23 +128,6 @@ template <int E>
 __device__ __forceinline__ void fast_window(const double* base, double (&win)[15]) {
 #pragma unroll
   for (int i = 0; i < 15; ++i) win[i] = base[(8 * E + 1 + i) + ((8 * E + 1 + i) >> 4)];
-}
-
-// exact (less, eq) of an element inside its bucket on the full key; returns less | eq << 16.
-// Kept out of line: it runs only for elements whose hi word collides with a bucket-mate's.
-template <bool TWO>
-__device__ __noinline__ unsigned resolve_exact(const unsigned* Khi, const unsigned* Klo, int st, int c, unsigned vhi,
-                                               unsigned vlo) {
-  unsigned less = 0, eq = 0;
-  for (int j = st; j < st + c; ++j) {
-    const unsigned yhi = Khi[j];
-    if (TWO) {
-      const unsigned ylo = Klo[j];
-      less += (yhi < vhi) | ((yhi == vhi) & (ylo < vlo));
-      eq += (yhi == vhi) & (ylo == vlo);
-    } else { less += (yhi < vhi); eq += (yhi == vhi); }
-  }
-  return less | (eq << 16);
 }
 
 // LONG = every split chain has more than 480 draws: only the last of a thread's 16 slots can be empty, so
