@@ -48,8 +48,10 @@ def gather_params(local, total: int, dst: int = 0, group=None):
 
 
 def sharded_call(fn, samples, group=None, dst: int = 0):
-    """Run `fn(shard) -> (ess, rhat)` on this rank's parameter shard of `samples`
-    (draws, chains, params) and gather the stacked results to `dst`."""
+    """Run `fn(shard)` on this rank's parameter shard of `samples` (draws, chains, params) and gather
+    the per-parameter results to `dst`.  `fn` may return one array, a tuple of arrays (e.g.
+    `(ess, rhat)`: gathered as a stacked `(k, params)` tensor) or a dict of arrays (e.g. `summary`:
+    gathered as a dict of `(params,)` tensors).  Returns None on the other ranks."""
     import torch
     import torch.distributed as dist
 
@@ -57,6 +59,21 @@ def sharded_call(fn, samples, group=None, dst: int = 0):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     total = samples.shape[2]
     lo, hi = shard_range(total, rank, world)
-    S, R = fn(samples[:, :, lo:hi])
-    out = torch.stack((torch.as_tensor(S), torch.as_tensor(R)))
-    return gather_params(out, total, dst=dst, group=group)
+    res = fn(samples[:, :, lo:hi])
+    keys = None
+    if isinstance(res, dict):
+        keys = list(res)
+        parts = [res[k] for k in keys]
+    elif isinstance(res, (tuple, list)):
+        parts = list(res)
+    else:
+        parts = [res]
+    out = torch.stack([torch.as_tensor(p).reshape(-1) for p in parts])
+    full = gather_params(out, total, dst=dst, group=group)
+    if full is None:
+        return None
+    if keys is not None:
+        return {k: full[i] for i, k in enumerate(keys)}
+    if not isinstance(res, (tuple, list)):
+        return full[0]
+    return full

@@ -24,13 +24,18 @@ def _worker(rank, world, port, total, tmp):
     out = m.sharding.sharded_call(lambda xs: o.ess_rhat(xs), x)
     lo, hi = m.sharding.shard_range(total, rank, world)
     assert (hi - lo) in (total // world, total // world + 1)
+    summ = m.sharding.sharded_call(lambda xs: o.summary(xs, fields=("mean", "ess_bulk", "rhat")), x)   # dict results
+    single = m.sharding.sharded_call(lambda xs: o.rhat(xs), x)                                           # one array
     if rank == 0:
         S, R = o.ess_rhat(x)
         assert out.shape == (2, total)
         assert np.array_equal(out[0].numpy(), S) and np.array_equal(out[1].numpy(), R)   # independent of W
+        want = o.summary(x, fields=("mean", "ess_bulk", "rhat"))
+        assert list(summ) == list(want) and all(np.array_equal(summ[k].numpy(), want[k]) for k in want)
+        assert np.array_equal(single.numpy(), o.rhat(x))
         open(os.path.join(tmp, f"ok{world}"), "w").write("ok")
     else:
-        assert out is None
+        assert out is None and summ is None and single is None
     dist.barrier()
     dist.destroy_process_group()
 
