@@ -20,6 +20,7 @@ using SpecialFunctions: SpecialFunctions
 export ess, ess_rhat, rhat, rhat_nested, mcse
 export summary_columns
 export gewekediag, heideldiag
+export bfmi, chain_moments
 export AutocovMethod, FFTAutocovMethod, BDAAutocovMethod
 export ESSMethod, FFTESSMethod, BDAESSMethod
 
@@ -337,6 +338,40 @@ function _pcramer(q::Real)
         p += SpecialFunctions.gamma(k + 0.5) / factorial(k) * sqrt(c1) * exp(-c2) * SpecialFunctions.besselk(0.25, c2)
     end
     return p / (pi^1.5 * sqrt(q))
+end
+
+
+# ---- SURVEY §8(f)4: moment kernels behind a different combine ----------------------------------------------
+"""`bfmi(energy; dims=1)` (src/bfmi.jl:36-43) on the device: one value per chain."""
+function bfmi(energy::AbstractVector{<:Real})
+    return first(bfmi(reshape(energy, :, 1)))
+end
+function bfmi(energy::AbstractMatrix{<:Real}; dims::Int=1)
+    T = float(eltype(energy)) === Float32 ? Float32 : Float64
+    e = Matrix{T}(dims == 1 ? energy : permutedims(energy))
+    out = Vector{T}(undef, size(e, 2))
+    GC.@preserve e out begin
+        rc = ccall((:mcd_bfmi, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Cvoid}),
+                   context(), e, MCD_HOST, _dtype(T), size(e, 1), size(e, 2), out)
+        _check(rc)
+    end
+    return out
+end
+
+"""Per split-chain means and corrected variances, `(chains * split_chains, params)` each: the quantities
+`_gelmandiag` (src/gelmandiag.jl:9-17) needs for `psrf` / `psrfci` (only the diagonals of W and B enter)."""
+function chain_moments(samples::AbstractArray{<:Real,3}; split_chains::Int=1)
+    T = float(eltype(samples)) === Float32 ? Float32 : Float64
+    x = Array{T,3}(samples)
+    nch, P = size(x, 2) * split_chains, size(x, 3)
+    m = Matrix{T}(undef, nch, P); v = Matrix{T}(undef, nch, P)
+    GC.@preserve x m v begin
+        rc = ccall((:mcd_chain_moments, LIB), Cint,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                   context(), x, MCD_HOST, _dtype(T), size(x, 1), size(x, 2), P, split_chains, m, v)
+        _check(rc)
+    end
+    return (mean=m, var=v)
 end
 
 end # module
