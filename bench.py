@@ -95,6 +95,15 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm on the host cores (oracle/ref_port.cpp)
 # ---------------------------------------------------------------------------------------------
+def host_threads():
+    """Host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 for its workers; the CPU arm
+    sets its own thread count (omp_set_num_threads), so the affinity mask is what counts."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample_params(cores):
     return max(2000, 1500 * cores)
 
@@ -112,7 +121,7 @@ def host_ar1(params, seed=1):
 def run_cpu(x, steps, warmup):
     """Times oracle/ref_port.cpp (all host threads) on the (draws, chains, sample) array x."""
     from oracle import ref_port as rp
-    cores = rp.max_threads()
+    cores = host_threads()
     for _ in range(warmup):
         rp.ess_rhat(x, kind="rank", nthreads=cores)
     t0 = time.perf_counter()
@@ -128,7 +137,7 @@ def reference_arm(args):
         return 0
     from oracle import build_oracle, ref_port as rp
     build_oracle.build()
-    cores = rp.max_threads()
+    cores = host_threads()
     sample = cpu_sample_params(cores)
     x = host_ar1(sample)
     value, cores, sec = run_cpu(x, max(1, args.steps), min(args.warmup, 1))
@@ -301,7 +310,7 @@ def gpu_arm(args):
     if world == 1 and not args.no_cpu:
         from oracle import build_oracle, ref_port as rp
         build_oracle.build()
-        cores = rp.max_threads()
+        cores = host_threads()
         sample = min(shard, cpu_sample_params(cores))
         xs = np.asfortranarray(x[:, :, :sample].cpu().numpy())
         v, cores, sec = run_cpu(xs, 1, 0)
