@@ -67,3 +67,51 @@ def test_host_side_argument_errors_need_no_gpu():
         m.rhat_nested(x, [1, 1, 1, 2])
     inds = m.api._validate_superchain_ids(["b", "a", "b", "a"], 4)
     assert inds.tolist() == [[1, 0], [3, 2]]
+
+
+def _header_prototypes():
+    """name -> list of parameter C types parsed from include/mcmcdiag_b200.h"""
+    hdr = open(os.path.join(ROOT, "include", "mcmcdiag_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b([A-Za-z_][\w\s\*]*?)\b(mcd_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = [a.strip() for a in m.group(3).replace("\n", " ").split(",")]
+        if args == ["void"] or args == [""]:
+            args = []
+        protos[m.group(2)] = args
+    return protos
+
+
+def _kind(ctype_decl):
+    """Coarse class of a C parameter declaration."""
+    d = ctype_decl
+    if "*" in d:
+        return "ptr"
+    if "double" in d:
+        return "double"
+    if "int64_t" in d or "uint64_t" in d or "long long" in d:
+        return "i64"
+    return "int"       # int, unsigned
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """Every ctypes signature has the header's arity and the same coarse type per argument, so that a
+    drifted binding is caught without a GPU."""
+    import ctypes as C
+    import mcmcdiag_b200 as m
+    protos = _header_prototypes()
+    assert set(protos) == set(m._lib.SIGNATURES)
+
+    def ckind(t):
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        if t is C.c_double:
+            return "double"
+        if t in (C.c_int64, C.c_uint64):
+            return "i64"
+        return "int"
+
+    for name, (_, argtypes) in m._lib.SIGNATURES.items():
+        want = [_kind(a) for a in protos[name]]
+        got = [ckind(t) for t in argtypes]
+        assert got == want, (name, got, want, protos[name])
