@@ -6,6 +6,7 @@
 #include "mcd_common.cuh"
 #include "mcd_slab.cuh"
 #include "mcd_fast.cuh"
+#include "mcd_rk2_api.cuh"
 #include "mcd_fastgen.cuh"
 #include "mcd_large.cuh"
 
@@ -27,6 +28,7 @@ struct mcd_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_switch = nullptr;   // orders the per-context scratch across a change of stream
   std::mutex mu;
   std::string err;
   int sm_count = 0;
@@ -50,6 +52,7 @@ struct mcd_ctx {
   int fast_pad_smem = 0;   // developer knob: extra dynamic shared memory (lowers CTAs/SM)
   int slab_wide = 1;       // developer knob: 512-thread general kernel for slabs that fit one CTA per SM only
   int fast_grid_mult = 0;  // developer knob: 0 = one CTA per parameter, k = persistent grid of k * 2 * SMs CTAs
+  int use_rk2 = 1;         // developer knob: 0 = round-1 register-resident kernel instead of the TMA-staged one
   // stats
   long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   int last_path = 0;
@@ -532,7 +535,12 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   if (rc) return rc;
   a.redo_count = ga.redo_count = ctx->d_redo; a.redo_list = ga.redo_list = ctx->d_redo + 1;
   CU(cudaMemsetAsync(ctx->d_redo, 0, sizeof(int), ctx->stream));
-  if (lean) {
+  if (lean && ctx->use_rk2 && ((uintptr_t)dx & 15u) == 0 && pg.maxlag <= RK_MAXLAG_CAP) {
+    // persistent CTAs, two per SM, each streaming its parameters through the bulk-copy pipeline
+    const int mult = ctx->fast_grid_mult > 0 ? ctx->fast_grid_mult : 1;
+    const unsigned grid = (unsigned)std::min<long long>(params, (long long)mult * 2 * ctx->sm_count);
+    CU(rk2_launch<T>(a, grid, (size_t)ctx->fast_pad_smem, ctx->stream));
+  } else if (lean) {
     const size_t smem = fast_smem_bytes<T>(pg.maxlag) + (size_t)ctx->fast_pad_smem;
     auto kern = g.niter > 32 * (FAST_EPT - 1) ? fast_kernel<T, true> : fast_kernel<T, false>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -976,6 +984,7 @@ void mcd_destroy(mcd_ctx* ctx) {
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
   }
+  if (ctx->ev_switch) cudaEventDestroy(ctx->ev_switch);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -986,7 +995,16 @@ const char* mcd_last_error(const mcd_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int mcd_set_stream(mcd_ctx* ctx, void* cuda_stream, int use_own) {
   if (!ctx) return MCD_EINVAL;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  ctx->stream = use_own ? ctx->own_stream : (cudaStream_t)cuda_stream;
+  cudaStream_t next = use_own ? ctx->own_stream : (cudaStream_t)cuda_stream;
+  if (next != ctx->stream) {
+    // Every call shares the context's scratch (status flags, redo list, cached z / twiddle tables, workspace):
+    // work queued on the new stream must not start before the work already queued on the old one is done.
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->ev_switch) CU(cudaEventCreateWithFlags(&ctx->ev_switch, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->ev_switch, ctx->stream));
+    CU(cudaStreamWaitEvent(next, ctx->ev_switch, 0));
+    ctx->stream = next;
+  }
   return MCD_OK;
 }
 
@@ -1008,6 +1026,7 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   else if (k == "workspace_bytes") { if (value < (1 << 20)) return fail(ctx, MCD_EINVAL, "workspace_bytes >= 1 MiB"); ctx->workspace_bytes = value; }
   else if (k == "fast_pad_smem") { ctx->fast_pad_smem = (int)value; }
   else if (k == "fast_grid_mult") { ctx->fast_grid_mult = (int)value; }
+  else if (k == "use_rk2") { ctx->use_rk2 = (int)value; }
   else if (k == "slab_wide") ctx->slab_wide = value ? 1 : 0;
   else if (k == "sort_bucket_limit") { if (value < 0) return fail(ctx, MCD_EINVAL, "sort_bucket_limit >= 0"); ctx->bucket_limit = (int)value; }
   else return fail(ctx, MCD_EINVAL, "unknown option '%s'", key);
