@@ -92,11 +92,27 @@ def test_c4_nested_fraction_within_tolerance(env):
 
 
 def test_c5_bda_float32_fraction_within_tolerance(env):
+    """Float32: the reference's formulas evaluated in Float32 carry ~1e-4 of arithmetic noise here (BDA variogram +
+    indicator proxy: `mean(var) - s / 2n` cancels to ~4 % of its operands and Geyer sums ~100 such terms): the NumPy
+    oracle's Float32 evaluation differs from its own Float64 evaluation of the same draws by up to 7e-5, and so would
+    any other Float32 summation order, Julia's included.  The CUDA path accumulates in Float64 and rounds where the
+    reference stores Float32, so it must sit within 1e-4 of the Float64 evaluation for EVERY parameter, and within
+    1e-4 + that noise of the Float32 oracle.  (This is the `1.08e-4` of round 1's cfg.log: noise, not a Geyer flip.)"""
+    import torch
+    from oracle import mcmcdiag_oracle as o
     bench, m = env
+    cfg = bench.CONFIGS["c5bda"]
     n = 1000
-    frac, worst, out = compare(bench, m, "c5bda", n, oracle_only=True)
-    print(f"C5 ess(median)+ess(std) BDA 4000x8 f32: {frac:.6f} of {n} parameters within 1e-4, worst {worst:.2e}, outliers {out}")
-    # Float32: a summation-order difference of ~1e-7 can flip one Geyer lag pair (`delta > 0`) of a rare parameter;
-    # everything else must be inside the tolerance and the flips must stay rare
-    assert frac >= 0.995, out
-    assert all(rel < 0.2 for *_, rel in out), out
+    x = m.generate_ar1(bench.PHI, np.sqrt(1 - bench.PHI ** 2), cfg.draws, cfg.chains, n, seed=1, dtype=cfg.dtype)
+    res = [r.double().cpu().numpy() for r in cfg.run(m, x)]
+    xs = np.asfortranarray(x.cpu().numpy())
+    exact, _, _ = cfg.run_cpu(xs, bench.host_threads())                 # the same formulas in Float64 (C++ port)
+    f32 = run_oracle("c5bda", xs[:, :, :200])                          # dtype-faithful Float32 oracle (slower)
+    for col, name in enumerate(("median", "std")):
+        rel64 = np.abs(res[col] - exact[col]) / np.abs(exact[col])
+        rel32 = np.abs(res[col][:200] - f32[col]) / np.abs(f32[col])
+        noise = np.abs(np.asarray(f32[col], dtype=np.float64) - exact[col][:200]) / np.abs(exact[col][:200])
+        print(f"C5 ess({name}) BDA 4000x8 f32: vs Float64 evaluation {np.mean(rel64 <= 1e-4):.6f} of {n} within 1e-4 (worst {rel64.max():.2e}); "
+              f"vs Float32 oracle worst {rel32.max():.2e}; the Float32 oracle's own noise vs Float64: worst {noise.max():.2e}")
+        assert (rel64 <= 1e-4).all(), np.flatnonzero(rel64 > 1e-4)
+        assert (rel32 <= 1e-4 + noise + 1e-6).all(), np.flatnonzero(rel32 > 1e-4 + noise + 1e-6)
