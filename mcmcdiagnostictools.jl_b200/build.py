@@ -13,11 +13,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libmcmcdiag_b200.so")
-COMMON = ["mcd_common.cuh", "mcd_slab.cuh", "mcd_fast.cuh", "mcd_rk2_api.cuh"]
+COMMON = ["mcd_common.cuh", "mcd_slab.cuh", "mcd_fast.cuh", "mcd_rk2_api.cuh", "mcd_big_api.cuh"]
 # translation unit -> headers it depends on (besides COMMON and the public header)
 UNITS = {
     "mcd_api.cu": ["mcd_fastgen.cuh", "mcd_large.cuh"],
-    "mcd_rk2.cu": ["mcd_rk2.cuh"],
+    "mcd_rk2.cu": ["mcd_rk2.cuh", "mcd_tma.cuh"],
+    "mcd_big.cu": ["mcd_big.cuh", "mcd_big_api.cuh", "mcd_tma.cuh"],
 }
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

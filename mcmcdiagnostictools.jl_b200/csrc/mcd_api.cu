@@ -7,6 +7,7 @@
 #include "mcd_slab.cuh"
 #include "mcd_fast.cuh"
 #include "mcd_rk2_api.cuh"
+#include "mcd_big_api.cuh"
 #include "mcd_fastgen.cuh"
 #include "mcd_large.cuh"
 
@@ -53,6 +54,7 @@ struct mcd_ctx {
   int slab_wide = 1;       // developer knob: 512-thread general kernel for slabs that fit one CTA per SM only
   int fast_grid_mult = 0;  // developer knob: 0 = one CTA per parameter, k = persistent grid of k * 2 * SMs CTAs
   int use_rk2 = 1;         // developer knob: 0 = round-1 register-resident kernel instead of the TMA-staged one
+  int use_big = 1;         // developer knob: 0 = never use the big-slab estimator kernel (mcd_big.cuh)
   // stats
   long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   int last_path = 0;
@@ -651,6 +653,39 @@ static int run_fast_summary(mcd_ctx* ctx, const T* dx, long long params, const S
   return MCD_OK;
 }
 
+// The big-slab estimator kernel (mcd_big.cuh): slabs too large for two CTAs of the general kernel per SM but small
+// enough to live in one SM's shared memory (e.g. 4000 x 8 Float32), estimator ESS with the mean / std / median proxies,
+// direct or BDA autocovariance.
+template <typename T>
+static int run_big(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom& g, const Program& pg,
+                   T* d_ess, T* d_rhat, bool* handled) {
+  *handled = false;
+  if (!ctx->use_big || pg.nsteps != 1 || pg.combine != CB_PLAIN || pg.want_arr || pg.chain_inds) return MCD_OK;
+  const Step& s0 = pg.steps[0];
+  if (s0.reduce != RD_ESS_RHAT) return MCD_OK;
+  int proxy;
+  if (s0.transform == TR_NONE) proxy = 0;
+  else if (s0.transform == TR_STDPROXY) proxy = 1;
+  else if (s0.transform == TR_IND_MEDIAN) proxy = 2;
+  else return MCD_OK;
+  const bool ess_live = pg.want_ess && !pg.ess_nan;
+  if (ess_live && pg.method != MCD_AUTOCOV_DIRECT && pg.method != MCD_AUTOCOV_BDA) return MCD_OK;
+  if ((size_t)g.n * sizeof(T) <= (64u << 10) || ((uintptr_t)dx & 15u) != 0) return MCD_OK;
+  BigArgs<T> a;
+  memset(&a, 0, sizeof a);
+  const size_t smem = big_smem_bytes<T>(g, pg.maxlag, &a.off_aux, &a.off_part, &a.off_small);
+  if (!smem || smem > (size_t)ctx->smem_optin) return MCD_OK;
+  a.x = dx; a.params = params; a.g = g; a.proxy = proxy; a.method = pg.method; a.maxlag = pg.maxlag;
+  a.relative = pg.relative; a.ess_nan = pg.ess_nan; a.want_ess = pg.want_ess ? 1 : 0;
+  a.rel_ess_max = rel_ess_max_of<T>((long long)g.niter * g.nch);
+  a.ess_out = pg.want_ess ? d_ess : nullptr; a.rhat_out = pg.want_rhat ? d_rhat : nullptr;
+  CU(big_launch<T>(a, (unsigned)std::min<long long>(params, ctx->sm_count), ctx->stream));
+  ctx->launches++;
+  ctx->last_path = 4;
+  *handled = true;
+  return MCD_OK;
+}
+
 // Run a program on device-resident data (params slabs).  Outputs are device pointers.
 template <typename T>
 static int run_device(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom& g, const Program& pg,
@@ -662,6 +697,11 @@ static int run_device(mcd_ctx* ctx, const T* dx, long long params, const SplitGe
     if (rc) return rc;
     if (handled) return MCD_OK;
     if (ctx->force_path == 3) return fail(ctx, MCD_EUNSUPPORTED, "this call is outside the fast kernel's shapes/programs");
+  }
+  if (ctx->force_path == 0) {
+    int rc = run_big<T>(ctx, dx, params, g, pg, d_ess, d_rhat, &handled);
+    if (rc) return rc;
+    if (handled) return MCD_OK;
   }
   if (ctx->force_path != 2) {
     int rc = run_slab<T>(ctx, dx, params, g, pg, d_ess, d_rhat, d_arr, &handled);
@@ -1027,6 +1067,7 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   else if (k == "fast_pad_smem") { ctx->fast_pad_smem = (int)value; }
   else if (k == "fast_grid_mult") { ctx->fast_grid_mult = (int)value; }
   else if (k == "use_rk2") { ctx->use_rk2 = (int)value; }
+  else if (k == "use_big") { ctx->use_big = (int)value; }
   else if (k == "slab_wide") ctx->slab_wide = value ? 1 : 0;
   else if (k == "sort_bucket_limit") { if (value < 0) return fail(ctx, MCD_EINVAL, "sort_bucket_limit >= 0"); ctx->bucket_limit = (int)value; }
   else return fail(ctx, MCD_EINVAL, "unknown option '%s'", key);

@@ -27,6 +27,7 @@
 #include "mcd_slab.cuh"
 #include "mcd_fast.cuh"
 #include "mcd_rk2_api.cuh"
+#include "mcd_tma.cuh"
 
 namespace mcd {
 
@@ -64,32 +65,6 @@ constexpr int RK_SMEM_BYTES = RK_OFF_SMALL + RK_SMALL_BYTES;
 static_assert(RK_A_FR >= RK_NCH * RK_ROW * 8, "FR must not overlap the centred rows");
 static_assert((RK_A_PART - RK_A_RHO) / 8 - (RK_LAGS + 1) >= RK_MAXLAG_CAP && RK_MAXLAG_CAP >= RK_MAXITER, "rho[] must hold every admissible maxlag");
 static_assert(RK_SEG * RK_THREADS >= RK_NMAX, "every merged value needs a thread");
-
-// ---- PTX: mbarrier + 1-D bulk async copy (TMA engine) ---------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_parity(unsigned mbar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "RK_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra RK_DONE;\n"
-      "bra RK_WAIT;\n"
-      "RK_DONE:\n"
-      "}\n" ::"r"(mbar), "r"(parity) : "memory");
-}
 
 template <typename T> __device__ __forceinline__ T rk_inf();
 template <> __device__ __forceinline__ double rk_inf<double>() { return CUDART_INF; }
