@@ -73,6 +73,15 @@ enum { MCD_EST_MEAN = 0, MCD_EST_MEDIAN = 1, MCD_EST_STD = 2, MCD_EST_MAD = 3, M
 /* Create a context bound to CUDA device `device` (one context per GPU; multi-GPU jobs
  * run one process or one context per GPU and shard the parameter axis). */
 int mcd_create(mcd_ctx** out, int device);
+/* Create ONE context that drives `ndev` GPUs of this process (distinct CUDA device ordinals).  Every hot-path call on
+ * it takes a HOST array (MCD_HOST), shards the parameter axis -- the reference's only parallel axis, the loops at
+ * src/ess_rhat.jl:380,517 and src/rhat_nested.jl:145 -- into `ndev` contiguous ranges, runs each range through its
+ * device's own pinned-staging pipeline on its own host thread, and writes every device's results into the matching
+ * range of the caller's single output buffer (results are independent of ndev).  This is how the Julia shim reaches all
+ * GPUs of a box with no torch / NCCL in the process (mcd_create(ctx**, devices, ndev)).  Device-resident
+ * input (MCD_DEVICE), mcd_set_stream and the device helpers below act on / belong to a single-device context; on a
+ * group the helpers are forwarded to its first device. */
+int mcd_create_multi(mcd_ctx** out, const int* devices, int ndev);
 void mcd_destroy(mcd_ctx* ctx);
 /* Last error message of this context ("" if none).  Valid until the next call on ctx. */
 const char* mcd_last_error(const mcd_ctx* ctx);
@@ -92,7 +101,7 @@ int mcd_synchronize(mcd_ctx* ctx);
  * "h2d_chunk_bytes", "workspace_bytes", "sort_bucket_limit". */
 int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value);
 /* Counters.  Keys: "kernel_launches" (since creation), "last_path" (1 slab, 2 large, 3 fast),
- * "h2d_bytes", "d2h_bytes", "sm_count", "smem_optin", "redo_count" (parameters the register-resident
+ * "h2d_bytes", "d2h_bytes", "sm_count", "smem_optin", "ndev" (devices of the context), "redo_count" (parameters the register-resident
  * kernel handed to the general kernel in the last launch: NaN, infinite range, heavy ties, ...). */
 int64_t mcd_get_stat(const mcd_ctx* ctx, const char* key);
 

@@ -31,6 +31,7 @@ SIGNATURES = {
     "mcd_abi_version": (_int, []),
     "mcd_create_error": (C.c_char_p, []),
     "mcd_create": (_int, [C.POINTER(_vp), _int]),
+    "mcd_create_multi": (_int, [C.POINTER(_vp), C.POINTER(_int), _int]),
     "mcd_destroy": (None, [_vp]),
     "mcd_last_error": (C.c_char_p, [_vp]),
     "mcd_set_stream": (_int, [_vp, _vp, _int]),

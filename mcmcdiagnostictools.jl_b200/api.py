@@ -99,15 +99,23 @@ class Quantile:
 # contexts
 # ---------------------------------------------------------------------------------------
 class Context:
-    """Owns one `mcd_ctx` (one per GPU)."""
+    """Owns one `mcd_ctx`: one GPU (`Context(device)`), or a multi-GPU group (`Context(devices=[0, 1, ...])`,
+    `mcd_create_multi`) that shards the parameter axis of HOST arrays over its devices inside the library."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None):
         self._lib = L.load()
         h = C.c_void_p()
-        rc = self._lib.mcd_create(C.byref(h), int(device))
+        if devices is not None:
+            devs = [int(d) for d in devices]
+            arr = (C.c_int * len(devs))(*devs)
+            rc = self._lib.mcd_create_multi(C.byref(h), arr, len(devs))
+            what = f"mcd_create_multi(devices={devs})"
+            device = devs[0] if devs else 0
+        else:
+            rc = self._lib.mcd_create(C.byref(h), int(device))
+            what = f"mcd_create(device={device})"
         if rc != L.MCD_OK:
-            raise L.MCDLibraryError(
-                f"mcd_create(device={device}) failed ({rc}): {self._lib.mcd_create_error().decode()}")
+            raise L.MCDLibraryError(f"{what} failed ({rc}): {self._lib.mcd_create_error().decode()}")
         self._h = h
         self.device = int(device)
 

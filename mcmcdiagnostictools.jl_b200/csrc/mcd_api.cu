@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace mcd;
@@ -27,6 +28,7 @@ using namespace mcd;
 // ---------------------------------------------------------------------------------------
 struct mcd_ctx {
   int device = 0;
+  std::vector<mcd_ctx*> children;   // non-empty: a multi-GPU group (mcd_create_multi); the group itself owns no device state
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_switch = nullptr;   // orders the per-context scratch across a change of stream
@@ -870,8 +872,50 @@ static int execute_jobs_t(mcd_ctx* ctx, const void* x, int mem, long long draws,
   return MCD_OK;
 }
 
+// A multi-GPU group (mcd_create_multi): parameters are independent (the reference's loops at src/ess_rhat.jl:380,517,
+// src/rhat_nested.jl:145), so device i of D gets the contiguous parameter range [i P / D, (i + 1) P / D) -- one
+// contiguous byte range of the column-major host array -- and writes its results straight into the same range of the
+// caller's output buffers.  One host thread per device drives that device's own staging pipeline; no collective is
+// needed because the results land in host memory.
+static int execute_jobs(mcd_ctx* ctx, const void* x, int mem, int dtype, long long draws, long long chains,
+                        long long params, int split, Job* jobs, int njobs);
+
+static int execute_jobs_multi(mcd_ctx* ctx, const void* x, int mem, int dtype, long long draws, long long chains,
+                              long long params, int split, Job* jobs, int njobs) {
+  if (mem != MCD_HOST)
+    return fail(ctx, MCD_EUNSUPPORTED, "a multi-GPU context takes host arrays (MCD_HOST); device-resident input belongs to one device's context");
+  if (dtype != MCD_F64 && dtype != MCD_F32) return fail(ctx, MCD_EINVAL, "bad dtype %d", dtype);
+  const size_t ts = dtype == MCD_F64 ? 8 : 4;
+  const int D = (int)ctx->children.size();
+  const size_t slab_bytes = (size_t)draws * (size_t)chains * ts;
+  std::vector<int> rcs(D, MCD_OK);
+  std::vector<std::thread> threads;
+  for (int d = 0; d < D; ++d) {
+    const long long lo = (long long)d * params / D, hi = (long long)(d + 1) * params / D;
+    if (hi == lo && params > 0) continue;
+    threads.emplace_back([=, &rcs]() {
+      mcd_ctx* c = ctx->children[d];
+      std::lock_guard<std::mutex> lk(c->mu);
+      c->err.clear();
+      std::vector<Job> sub(jobs, jobs + njobs);
+      for (Job& jb : sub) {
+        if (jb.out0) jb.out0 = (char*)jb.out0 + (size_t)lo * ts;
+        if (jb.out1) jb.out1 = (char*)jb.out1 + (size_t)lo * ts;
+        if (jb.arr) jb.arr = (char*)jb.arr + (size_t)lo * (size_t)draws * (size_t)chains * (size_t)jb.pg.arr_elem_bytes;
+      }
+      rcs[d] = execute_jobs(c, (const char*)x + (size_t)lo * slab_bytes, mem, dtype, draws, chains, hi - lo, split,
+                            sub.data(), njobs);
+    });
+  }
+  for (auto& t : threads) t.join();
+  for (int d = 0; d < D; ++d)
+    if (rcs[d] != MCD_OK) return fail(ctx, rcs[d], "device %d: %s", ctx->children[d]->device, ctx->children[d]->err.c_str());
+  return MCD_OK;
+}
+
 static int execute_jobs(mcd_ctx* ctx, const void* x, int mem, int dtype, long long draws, long long chains,
                         long long params, int split, Job* jobs, int njobs) {
+  if (!ctx->children.empty()) return execute_jobs_multi(ctx, x, mem, dtype, draws, chains, params, split, jobs, njobs);
   if (dtype == MCD_F64) return execute_jobs_t<double>(ctx, x, mem, draws, chains, params, split, jobs, njobs);
   if (dtype == MCD_F32) return execute_jobs_t<float>(ctx, x, mem, draws, chains, params, split, jobs, njobs);
   return fail(ctx, MCD_EINVAL, "bad dtype %d", dtype);
@@ -1013,8 +1057,38 @@ int mcd_create(mcd_ctx** out, int device) {
   return MCD_OK;
 }
 
+int mcd_create_multi(mcd_ctx** out, const int* devices, int ndev) {
+  if (!out || !devices || ndev < 1) return MCD_EINVAL;
+  *out = nullptr;
+  for (int i = 0; i < ndev; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) return fail(nullptr, MCD_EINVAL, "device %d listed twice", devices[i]);
+  mcd_ctx* grp = new (std::nothrow) mcd_ctx();
+  if (!grp) return MCD_ENOMEM;
+  grp->device = devices[0];
+  for (int i = 0; i < ndev; ++i) {
+    mcd_ctx* c = nullptr;
+    const int rc = mcd_create(&c, devices[i]);
+    if (rc != MCD_OK) {
+      for (mcd_ctx* k : grp->children) mcd_destroy(k);
+      delete grp;
+      return rc;   // g_create_err holds the message
+    }
+    grp->children.push_back(c);
+  }
+  grp->sm_count = grp->children[0]->sm_count;
+  grp->smem_optin = grp->children[0]->smem_optin;
+  *out = grp;
+  return MCD_OK;
+}
+
 void mcd_destroy(mcd_ctx* ctx) {
   if (!ctx) return;
+  if (!ctx->children.empty()) {
+    for (mcd_ctx* c : ctx->children) mcd_destroy(c);
+    delete ctx;
+    return;
+  }
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   void* ptrs[] = {ctx->ztab, ctx->tw, ctx->d_flags, ctx->d_chain_inds, ctx->d_redo, ctx->stage[0], ctx->stage[1],
@@ -1035,6 +1109,10 @@ const char* mcd_last_error(const mcd_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int mcd_set_stream(mcd_ctx* ctx, void* cuda_stream, int use_own) {
   if (!ctx) return MCD_EINVAL;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->children.empty()) {
+    if (use_own) return MCD_OK;   // every device of a group always runs on its own streams
+    return fail(ctx, MCD_EUNSUPPORTED, "a multi-GPU context runs on its devices' own streams");
+  }
   cudaStream_t next = use_own ? ctx->own_stream : (cudaStream_t)cuda_stream;
   if (next != ctx->stream) {
     // Every call shares the context's scratch (status flags, redo list, cached z / twiddle tables, workspace):
@@ -1050,6 +1128,10 @@ int mcd_set_stream(mcd_ctx* ctx, void* cuda_stream, int use_own) {
 
 int mcd_synchronize(mcd_ctx* ctx) {
   if (!ctx) return MCD_EINVAL;
+  if (!ctx->children.empty()) {
+    for (mcd_ctx* c : ctx->children) { const int rc = mcd_synchronize(c); if (rc) return rc; }
+    return MCD_OK;
+  }
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1059,6 +1141,13 @@ int mcd_synchronize(mcd_ctx* ctx) {
 
 int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return MCD_EINVAL;
+  if (!ctx->children.empty()) {
+    for (mcd_ctx* c : ctx->children) {
+      const int rc = mcd_set_option(c, key, value);
+      if (rc) return fail(ctx, rc, "%s", c->err.c_str());
+    }
+    return MCD_OK;
+  }
   std::lock_guard<std::mutex> lk(ctx->mu);
   std::string k(key);
   if (k == "force_path") { if (value < 0 || value > 3) return fail(ctx, MCD_EINVAL, "force_path in 0..3"); ctx->force_path = (int)value; }
@@ -1077,6 +1166,15 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
 int64_t mcd_get_stat(const mcd_ctx* ctx, const char* key) {
   if (!ctx || !key) return -1;
   std::string k(key);
+  if (k == "ndev") return ctx->children.empty() ? 1 : (int64_t)ctx->children.size();
+  if (!ctx->children.empty()) {
+    if (k == "kernel_launches" || k == "h2d_bytes" || k == "d2h_bytes" || k == "redo_count") {
+      int64_t tot = 0;
+      for (const mcd_ctx* c : ctx->children) { const int64_t v = mcd_get_stat(c, key); if (v < 0) return v; tot += v; }
+      return tot;
+    }
+    return mcd_get_stat(ctx->children[0], key);
+  }
   if (k == "kernel_launches") return ctx->launches;
   if (k == "last_path") return ctx->last_path;
   if (k == "h2d_bytes") return ctx->h2d_bytes;
@@ -1303,6 +1401,7 @@ int mcd_fold_around_median(mcd_ctx* ctx, const void* x, int mem, int dtype, int6
 int mcd_chain_moments(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t draws, int64_t chains, int64_t params,
                       int split_chains, void* mean_out, void* var_out) {
   if (!ctx) return MCD_EINVAL;
+  if (!ctx->children.empty()) { const int rc_ = mcd_chain_moments(ctx->children[0], x, mem, dtype, draws, chains, params, split_chains, mean_out, var_out); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->err.clear();
   if (!mean_out && !var_out) return fail(ctx, MCD_EINVAL, "both outputs are NULL");
@@ -1317,6 +1416,7 @@ int mcd_chain_moments(mcd_ctx* ctx, const void* x, int mem, int dtype, int64_t d
 
 int mcd_bfmi(mcd_ctx* ctx, const void* energy, int mem, int dtype, int64_t draws, int64_t chains, void* out) {
   if (!ctx) return MCD_EINVAL;
+  if (!ctx->children.empty()) { const int rc_ = mcd_bfmi(ctx->children[0], energy, mem, dtype, draws, chains, out); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->err.clear();
   if (!energy || !out) return fail(ctx, MCD_EINVAL, "NULL argument");
@@ -1329,6 +1429,7 @@ int mcd_bfmi(mcd_ctx* ctx, const void* energy, int mem, int dtype, int64_t draws
 int mcd_generate_ar1(mcd_ctx* ctx, int dtype, int64_t draws, int64_t chains, int64_t params, int64_t param_offset,
                      double phi, double sigma, uint64_t seed, void* dev_x) {
   if (!ctx) return MCD_EINVAL;
+  if (!ctx->children.empty()) { const int rc_ = mcd_generate_ar1(ctx->children[0], dtype, draws, chains, params, param_offset, phi, sigma, seed, dev_x); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->err.clear();
   if (!dev_x || draws <= 0 || chains <= 0 || params < 0) return fail(ctx, MCD_EINVAL, "bad argument");
@@ -1348,6 +1449,7 @@ int mcd_generate_ar1(mcd_ctx* ctx, int dtype, int64_t draws, int64_t chains, int
 
 int mcd_device_alloc(mcd_ctx* ctx, int64_t bytes, void** dev_ptr) {
   if (!ctx || !dev_ptr || bytes < 0) return MCD_EINVAL;
+  if (!ctx->children.empty()) { const int rc_ = mcd_device_alloc(ctx->children[0], bytes, dev_ptr); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   CU(cudaMalloc(dev_ptr, (size_t)std::max<int64_t>(bytes, 1)));
@@ -1355,6 +1457,7 @@ int mcd_device_alloc(mcd_ctx* ctx, int64_t bytes, void** dev_ptr) {
 }
 int mcd_device_free(mcd_ctx* ctx, void* dev_ptr) {
   if (!ctx) return MCD_EINVAL;
+  if (!ctx->children.empty()) { const int rc_ = mcd_device_free(ctx->children[0], dev_ptr); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   CU(cudaFree(dev_ptr));
@@ -1362,6 +1465,7 @@ int mcd_device_free(mcd_ctx* ctx, void* dev_ptr) {
 }
 int mcd_memcpy_h2d(mcd_ctx* ctx, void* dev_dst, const void* host_src, int64_t bytes) {
   if (!ctx) return MCD_EINVAL;
+  if (!ctx->children.empty()) { const int rc_ = mcd_memcpy_h2d(ctx->children[0], dev_dst, host_src, bytes); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   CU(cudaMemcpyAsync(dev_dst, host_src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -1370,6 +1474,7 @@ int mcd_memcpy_h2d(mcd_ctx* ctx, void* dev_dst, const void* host_src, int64_t by
 }
 int mcd_memcpy_d2h(mcd_ctx* ctx, void* host_dst, const void* dev_src, int64_t bytes) {
   if (!ctx) return MCD_EINVAL;
+  if (!ctx->children.empty()) { const int rc_ = mcd_memcpy_d2h(ctx->children[0], host_dst, dev_src, bytes); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   CU(cudaMemcpyAsync(host_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1378,6 +1483,7 @@ int mcd_memcpy_d2h(mcd_ctx* ctx, void* host_dst, const void* dev_src, int64_t by
 }
 int mcd_host_alloc(mcd_ctx* ctx, int64_t bytes, void** host_ptr) {
   if (!ctx || !host_ptr || bytes < 0) return MCD_EINVAL;
+  if (!ctx->children.empty()) { const int rc_ = mcd_host_alloc(ctx->children[0], bytes, host_ptr); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   CU(cudaHostAlloc(host_ptr, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
@@ -1385,6 +1491,7 @@ int mcd_host_alloc(mcd_ctx* ctx, int64_t bytes, void** host_ptr) {
 }
 int mcd_host_free(mcd_ctx* ctx, void* host_ptr) {
   if (!ctx) return MCD_EINVAL;
+  if (!ctx->children.empty()) { const int rc_ = mcd_host_free(ctx->children[0], host_ptr); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaFreeHost(host_ptr));
   return MCD_OK;
