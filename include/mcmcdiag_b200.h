@@ -96,6 +96,13 @@ int mcd_set_stream(mcd_ctx* ctx, void* cuda_stream, int use_own);
 /* Block until all work queued by this context has finished. */
 int mcd_synchronize(mcd_ctx* ctx);
 
+/* Per-parameter skip mask for the NEXT hot-path call on this context (consumed by it): parameters with skip[p] != 0
+ * are not computed -- their bytes are never copied to the device or read -- and their outputs are NaN.  This is the
+ * reference's `missing` handling (a parameter containing `missing` yields `missing`, src/ess_rhat.jl:382-385,519-523)
+ * without a compacted copy of the samples: the host shim passes the array as it is (any finite filler in the masked
+ * entries) and maps the NaNs of masked parameters back to `missing`.  `params` must equal the call's parameter count. */
+int mcd_set_param_mask(mcd_ctx* ctx, const unsigned char* skip, int64_t params);
+
 /* Tuning / test knobs.  Keys: "force_path" (0 auto, 1 general shared-memory slab kernel,
  * 2 global-memory large-slab pipeline, 3 register-resident fast kernel only),
  * "h2d_chunk_bytes", "workspace_bytes", "sort_bucket_limit". */

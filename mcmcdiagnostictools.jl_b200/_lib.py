@@ -36,6 +36,7 @@ SIGNATURES = {
     "mcd_last_error": (C.c_char_p, [_vp]),
     "mcd_set_stream": (_int, [_vp, _vp, _int]),
     "mcd_synchronize": (_int, [_vp]),
+    "mcd_set_param_mask": (_int, [_vp, C.POINTER(C.c_ubyte), _i64]),
     "mcd_set_option": (_int, [_vp, C.c_char_p, _i64]),
     "mcd_get_stat": (_i64, [_vp, C.c_char_p]),
     "mcd_ess_rhat": (_int, _SHAPE + [_int, _int, _int, _int, _int, _dbl, _int, _vp, _vp]),

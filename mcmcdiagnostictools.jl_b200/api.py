@@ -160,6 +160,24 @@ class Context:
         self.check(self._lib.mcd_synchronize(self._h))
 
 
+def _default_host_device() -> int:
+    """Device for host (NumPy) input when no context is passed: the process's current CUDA device if torch is loaded
+    (torchrun workers set it from LOCAL_RANK), else LOCAL_RANK, else 0."""
+    import os
+    import sys
+    t = sys.modules.get("torch")
+    if t is not None:
+        try:
+            if t.cuda.is_available():
+                return int(t.cuda.current_device())
+        except Exception:
+            pass
+    try:
+        return int(os.environ.get("LOCAL_RANK", "0"))
+    except ValueError:
+        return 0
+
+
 _contexts: dict[int, Context] = {}
 _ctx_lock = threading.Lock()
 
@@ -208,14 +226,15 @@ class _Arr:
         self.scalar = x.ndim < 3
         x3 = np.asfortranarray(x.astype(dt, copy=False)).reshape(shape3, order="F")
         if mask is not None and mask.any():
+            # a parameter that contains `missing` yields `missing` (src/ess_rhat.jl:382-385,519-523): the library gets the
+            # array as it is plus a per-parameter skip mask (mcd_set_param_mask); no compacted copy is made
             m3 = np.asfortranarray(mask).reshape(shape3, order="F")
             self.missing = m3.any(axis=(0, 1))
-            x3 = np.asfortranarray(x3[:, :, ~self.missing])
         self.x3 = x3
         self.mem = L.MCD_HOST
         self.ptr = x3.ctypes.data if x3.size else 0
         self.nparams = x3.shape[2]
-        self.device = 0
+        self.device = _default_host_device()
 
     # torch CUDA tensors: device memory
     def _init_torch(self, samples):
@@ -277,9 +296,7 @@ class _Arr:
                 return o.reshape(())
             return o.reshape(tuple(reversed(self.pshape))).permute(*reversed(range(len(self.pshape))))
         if self.missing is not None:
-            full = np.ma.masked_all(self.P, dtype=self.dtype)
-            full[~self.missing] = o
-            o = full
+            o = np.ma.array(o, mask=self.missing)
         if self.scalar:
             v = o.reshape(())[()]
             return v if v is np.ma.masked else self.dtype.type(v)
@@ -292,6 +309,9 @@ class _Arr:
             ctx.set_stream(torch.cuda.current_stream(self.torch_device).cuda_stream)
         else:
             ctx.set_stream(None)
+        if self.missing is not None:
+            skip = np.ascontiguousarray(self.missing, dtype=np.uint8)
+            ctx.check(ctx._lib.mcd_set_param_mask(ctx._h, skip.ctypes.data_as(C.POINTER(C.c_ubyte)), skip.size))
         return ctx
 
 
@@ -368,6 +388,11 @@ def _call_ess_rhat(a, kind, want_ess, want_rhat, relative=False, autocov_method=
     return a.finish(e), a.finish(r)
 
 
+def _clamp_maxlag(maxlag) -> int:
+    """maxlag as a C int: ctypes would otherwise truncate modulo 2^32 (the library clamps to niter - 4 anyway)."""
+    return int(max(min(int(maxlag), 2**31 - 1), -1))
+
+
 def _call_estimator(a, est, relative=False, autocov_method=None, split_chains=2, maxlag=250, ctx=None,
                     mcse_mode=False):
     _check_split(split_chains)
@@ -380,11 +405,11 @@ def _call_estimator(a, est, relative=False, autocov_method=None, split_chains=2,
     out = a.new_out()
     if mcse_mode:
         rc = ctx._lib.mcd_mcse(ctx._h, C.c_void_p(a.ptr), a.mem, a.code, a.draws, a.chains, a.nparams,
-                               L.ESTIMATORS[name], p, int(p64), method, int(split_chains), int(maxlag),
+                               L.ESTIMATORS[name], p, int(p64), method, int(split_chains), _clamp_maxlag(maxlag),
                                a.out_ptr(out))
     else:
         rc = ctx._lib.mcd_ess_estimator(ctx._h, C.c_void_p(a.ptr), a.mem, a.code, a.draws, a.chains, a.nparams,
-                                        L.ESTIMATORS[name], p, int(p64), method, int(split_chains), int(maxlag),
+                                        L.ESTIMATORS[name], p, int(p64), method, int(split_chains), _clamp_maxlag(maxlag),
                                         int(bool(relative)), a.out_ptr(out))
     ctx.check(rc, domain=True)
     return a.finish(out)
@@ -430,19 +455,75 @@ def ess_rhat(samples, *, kind="rank", ctx=None, **kwargs):
     return ESSRhat(e, r)
 
 
+def _mad(v, axis=None):
+    """StatsBase.mad(x) (normalize = true): 1.4826... * median(|x - median(x)|)."""
+    med = np.median(v, axis=axis, keepdims=axis is not None)
+    return 1.4826022185056018 * np.median(np.abs(v - med), axis=axis)
+
+
+def _mcse_sbm(f, samples, batch_size=None):
+    """`_mcse_sbm(f, x; batch_size)` (src/mcse.jl:120-148): the subsampling-bootstrap fallback for estimators without
+    an ESS rule.  As in the reference it is host logic: `f` is an arbitrary host callable evaluated on every
+    overlapping batch of the flattened draws, so nothing of it can cross the C ABI."""
+    masked = isinstance(samples, np.ma.MaskedArray)
+    mask = np.ma.getmaskarray(samples) if masked else None
+    x = np.asarray(samples.filled(0) if masked else samples)
+    if type(samples).__module__.startswith("torch"):
+        x = samples.detach().cpu().numpy()
+    T = np.float32 if x.dtype == np.float32 else np.float64
+    draws = x.shape[0]
+    chains = x.shape[1] if x.ndim > 1 else 1
+    pshape = tuple(x.shape[2:])
+    x3 = np.asfortranarray(x.astype(T, copy=False)).reshape((draws, chains, -1), order="F")
+    m3 = None if mask is None else np.asfortranarray(mask).reshape((draws, chains, -1), order="F")
+    n = draws * chains
+    b = int(math.floor(math.sqrt(n))) if batch_size is None else int(batch_size)
+    out = np.empty(x3.shape[2], dtype=T)
+    miss = np.zeros(x3.shape[2], dtype=bool)
+    for p in range(x3.shape[2]):
+        v = x3[:, :, p].reshape(-1, order="F")
+        if m3 is not None and m3[:, :, p].any():
+            miss[p] = True
+            out[p] = np.nan
+            continue
+        if np.all(v == v[0]):
+            out[p] = np.nan
+            continue
+        win = np.lib.stride_tricks.sliding_window_view(v, b)
+        try:
+            vals = np.asarray(f(win, axis=1), dtype=np.float64)
+            if vals.shape != (win.shape[0],):
+                raise TypeError
+        except TypeError:
+            vals = np.array([f(w) for w in win], dtype=np.float64)
+        out[p] = T(math.sqrt(vals.var() * (b / n)))
+    if x.ndim < 3:
+        return np.ma.masked if miss[0] else T(out[0])
+    res = np.ma.array(out, mask=miss) if miss.any() else out
+    return res.reshape(pshape, order="F")
+
+
 def mcse(samples, *, kind=np.mean, ctx=None, **kwargs):
     """`mcse(samples; kind=Statistics.mean, kwargs...)`  (src/mcse.jl:5-42).
 
-    mean / std / median / quantile use the ESS-based rules on the GPU.  Any other estimator
-    uses the reference's subsampling-bootstrap fallback (src/mcse.jl:120-148), which calls a
-    user closure per window and therefore stays on the host (out of scope)."""
+    mean / std / median / quantile use the ESS-based rules on the GPU (src/mcse.jl:45-118).  Any other estimator
+    (`mad`, an arbitrary callable) uses the reference's subsampling-bootstrap fallback `_mcse_sbm`
+    (src/mcse.jl:120-148; keyword `batch_size`), which evaluates a host callable per batch and therefore runs on the host
+    here exactly as it does in the reference."""
     est = _estimator(kind)
     if est is None or est[0] == "mad":
-        raise NotImplementedError(
-            "mcse for this estimator uses the subsampling bootstrap (SBM) of the reference, "
-            "which stays in the host language and is outside the accelerated path")
+        f = _mad if (est is not None or kind in ("mad", "abs", "folded")) else kind
+        if not callable(f):
+            raise ArgumentError(f"the estimator {kind!r} is not supported by `mcse`")
+        extra = set(kwargs) - {"batch_size"}
+        if extra:
+            raise TypeError(f"mcse() got unexpected keyword arguments {sorted(extra)} for the subsampling-bootstrap fallback")
+        return _mcse_sbm(f, samples, kwargs.get("batch_size"))
+    if kwargs.pop("relative", False):
+        # the reference forwards `relative` to `_ess`, i.e. it would plug the RELATIVE effective sample size into the
+        # standard-error rules; the C ABI's mcd_mcse has no such mode, so it is rejected rather than ignored
+        raise NotImplementedError("mcse(...; relative=true) is not supported by the accelerated path")
     a = _Arr(samples)
-    kwargs.pop("relative", None)
     return _call_estimator(a, est, ctx=ctx, mcse_mode=True, **kwargs)
 
 
@@ -544,8 +625,12 @@ def _transform(samples, fn_name, out_dtype, ctx=None):
     rc = getattr(ctx._lib, fn_name)(ctx._h, C.c_void_p(a.ptr), a.mem, a.code, a.draws, a.chains, a.nparams, ptr)
     ctx.check(rc)
     if a.is_torch:
-        out = out.permute(2, 1, 0)
-        return out.reshape((a.draws, a.chains) + a.pshape) if len(a.pshape) != 1 else out
+        # the library wrote (params, chains, draws) C-contiguous with the parameter axis flattened in column-major order
+        # (as `_init_torch` / `finish` flatten it): view it as (*reversed(pshape), chains, draws) and reverse all axes
+        nd = np.ndim(samples) if not hasattr(samples, "ndim") else samples.ndim
+        full = out.reshape(tuple(reversed(a.pshape)) + (a.chains, a.draws))
+        full = full.permute(*reversed(range(full.ndim)))          # (draws, chains, *pshape)
+        return full.reshape(a.draws) if nd == 1 else full
     full_shape = (a.draws,) + ((a.chains,) if np.ndim(samples) > 1 else ()) + a.pshape
     return out.reshape(full_shape, order="F")
 

@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -29,6 +30,7 @@ using namespace mcd;
 struct mcd_ctx {
   int device = 0;
   std::vector<mcd_ctx*> children;   // non-empty: a multi-GPU group (mcd_create_multi); the group itself owns no device state
+  std::vector<unsigned char> skip;  // per-parameter skip mask of the NEXT hot-path call (mcd_set_param_mask); empty = none
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_switch = nullptr;   // orders the per-context scratch across a change of stream
@@ -189,6 +191,11 @@ struct Job {
   void* out1 = nullptr;   // rhat / std
   void* arr = nullptr;    // per-element output of the transform calls
 };
+
+// NaN for the outputs of skipped parameters (mcd_set_param_mask) when the outputs live in device memory.
+template <typename T> __global__ void fill_kernel(T* out, long long n, T v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = v;
+}
 
 // Statistics.mean(x; dims=(1,2)) and Statistics.std(x; dims=(1,2)) (the quantities src/mcse.jl:50
 // uses), one CTA per parameter, two passes in double; NaN propagates.
@@ -913,8 +920,66 @@ static int execute_jobs_multi(mcd_ctx* ctx, const void* x, int mem, int dtype, l
   return MCD_OK;
 }
 
+// Per-parameter skip mask (the reference skips parameters that contain `missing`, src/ess_rhat.jl:382-385,519-523):
+// the call runs on the maximal runs of kept parameters -- contiguous byte ranges of the caller's array, so a skipped
+// parameter is never copied, staged or read -- and the outputs of skipped parameters are NaN (the shim turns them
+// into `missing`).  No compacted copy of the samples is made anywhere.
+template <typename T>
+static int fill_skipped(mcd_ctx* ctx, int mem, void* out, long long lo, long long cnt) {
+  if (!out || cnt <= 0) return MCD_OK;
+  T* o = (T*)out + lo;
+  const T nanv = std::numeric_limits<T>::quiet_NaN();
+  if (mem == MCD_HOST) { for (long long i = 0; i < cnt; ++i) o[i] = nanv; return MCD_OK; }
+  mcd_ctx* c = ctx->children.empty() ? ctx : ctx->children[0];
+  CU(cudaSetDevice(c->device));
+  fill_kernel<T><<<(unsigned)std::min<long long>((cnt + 255) / 256, 4096), 256, 0, c->stream>>>(o, cnt, nanv);
+  CU(cudaGetLastError());
+  return MCD_OK;
+}
+
+static int execute_jobs_masked(mcd_ctx* ctx, const void* x, int mem, int dtype, long long draws, long long chains,
+                               long long params, int split, Job* jobs, int njobs) {
+  std::vector<unsigned char> skip;
+  skip.swap(ctx->skip);   // consumed by this call
+  if ((long long)skip.size() != params)
+    return fail(ctx, MCD_EINVAL, "the parameter mask has %lld entries but the call has %lld parameters", (long long)skip.size(), params);
+  if (dtype != MCD_F64 && dtype != MCD_F32) return fail(ctx, MCD_EINVAL, "bad dtype %d", dtype);
+  const size_t ts = dtype == MCD_F64 ? 8 : 4;
+  const size_t slab_bytes = (size_t)draws * (size_t)chains * ts;
+  long long p = 0;
+  while (p < params) {
+    long long q = p;
+    const bool skipped = skip[p] != 0;
+    while (q < params && (skip[q] != 0) == skipped) ++q;
+    std::vector<Job> sub(jobs, jobs + njobs);
+    for (Job& jb : sub) {
+      if (skipped) {
+        int rc = dtype == MCD_F64 ? fill_skipped<double>(ctx, mem, jb.out0, p, q - p) : fill_skipped<float>(ctx, mem, jb.out0, p, q - p);
+        if (!rc) rc = dtype == MCD_F64 ? fill_skipped<double>(ctx, mem, jb.out1, p, q - p) : fill_skipped<float>(ctx, mem, jb.out1, p, q - p);
+        if (rc) return rc;
+        if (jb.arr) {   // per-element outputs of the transform calls: arr_elem_bytes is 4 or 8
+          const long long e0 = p * draws * chains, ec = (q - p) * draws * chains;
+          rc = jb.pg.arr_elem_bytes == 8 ? fill_skipped<double>(ctx, mem, jb.arr, e0, ec) : fill_skipped<float>(ctx, mem, jb.arr, e0, ec);
+          if (rc) return rc;
+        }
+        continue;
+      }
+      if (jb.out0) jb.out0 = (char*)jb.out0 + (size_t)p * ts;
+      if (jb.out1) jb.out1 = (char*)jb.out1 + (size_t)p * ts;
+      if (jb.arr) jb.arr = (char*)jb.arr + (size_t)p * (size_t)draws * (size_t)chains * (size_t)jb.pg.arr_elem_bytes;
+    }
+    if (!skipped) {
+      const int rc = execute_jobs(ctx, (const char*)x + (size_t)p * slab_bytes, mem, dtype, draws, chains, q - p, split, sub.data(), njobs);
+      if (rc) return rc;
+    }
+    p = q;
+  }
+  return MCD_OK;
+}
+
 static int execute_jobs(mcd_ctx* ctx, const void* x, int mem, int dtype, long long draws, long long chains,
                         long long params, int split, Job* jobs, int njobs) {
+  if (!ctx->skip.empty()) return execute_jobs_masked(ctx, x, mem, dtype, draws, chains, params, split, jobs, njobs);
   if (!ctx->children.empty()) return execute_jobs_multi(ctx, x, mem, dtype, draws, chains, params, split, jobs, njobs);
   if (dtype == MCD_F64) return execute_jobs_t<double>(ctx, x, mem, draws, chains, params, split, jobs, njobs);
   if (dtype == MCD_F32) return execute_jobs_t<float>(ctx, x, mem, draws, chains, params, split, jobs, njobs);
@@ -1136,6 +1201,16 @@ int mcd_synchronize(mcd_ctx* ctx) {
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->copy_stream));
+  return MCD_OK;
+}
+
+int mcd_set_param_mask(mcd_ctx* ctx, const unsigned char* skip, int64_t params) {
+  if (!ctx || params < 0 || (params > 0 && !skip)) return MCD_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->skip.assign(skip, skip + params);
+  bool any = false;
+  for (int64_t i = 0; i < params && !any; ++i) any = skip[i] != 0;
+  if (!any) ctx->skip.clear();   // nothing to skip: the plain path
   return MCD_OK;
 }
 

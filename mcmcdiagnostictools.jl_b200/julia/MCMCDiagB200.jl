@@ -15,11 +15,9 @@ module MCMCDiagB200
 
 using Statistics: Statistics
 using StatsBase: StatsBase
-using SpecialFunctions: SpecialFunctions
 
 export ess, ess_rhat, rhat, rhat_nested, mcse
 export summary_columns
-export gewekediag, heideldiag
 export bfmi, chain_moments
 export AutocovMethod, FFTAutocovMethod, BDAAutocovMethod
 export ESSMethod, FFTESSMethod, BDAESSMethod
@@ -42,12 +40,22 @@ _dtype(::Type{Float32}) = Cint(0)
 _dtype(::Type{Float64}) = Cint(1)
 const KIND = Dict(:basic => Cint(0), :bulk => Cint(1), :tail => Cint(2), :rank => Cint(3))
 
-# ---- context (one per GPU, created lazily) -------------------------------------------------
+# ---- context (created lazily) -----------------------------------------------------------------
+# One GPU by default (device 0, or ENV["MCMCDIAG_B200_DEVICES"] = "3"); with several ordinals,
+# ENV["MCMCDIAG_B200_DEVICES"] = "0,1,2,3,4,5,6,7", ONE multi-GPU context (mcd_create_multi) shards the parameter axis of
+# every host array over the listed GPUs inside the library: no CUDA.jl, no NCCL, no extra processes on the Julia side.
 const _ctx = Ref{Ptr{Cvoid}}(C_NULL)
-function context(device::Integer=0)
+function _devices()
+    spec = get(ENV, "MCMCDIAG_B200_DEVICES", "0")
+    return Cint[parse(Cint, strip(t)) for t in split(spec, ',') if !isempty(strip(t))]
+end
+function context()
     if _ctx[] == C_NULL
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:mcd_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), h, device)
+        devs = _devices()
+        rc = length(devs) == 1 ?
+            ccall((:mcd_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), h, devs[1]) :
+            ccall((:mcd_create_multi, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cint}, Cint), h, devs, length(devs))
         rc == 0 || error("mcd_create failed ($rc): " * unsafe_string(ccall((:mcd_create_error, LIB), Cstring, ())))
         _ctx[] = h[]
         atexit(() -> ccall((:mcd_destroy, LIB), Cvoid, (Ptr{Cvoid},), _ctx[]))
@@ -76,39 +84,50 @@ _maybescalar(x::AbstractArray{<:Any,0}) = x[]
 _maybescalar(x::AbstractArray) = x
 _floattype(x) = promote_type(nonmissingtype(eltype(x)), typeof(zero(nonmissingtype(eltype(x))) / 1))
 
-# dense column-major (draws, chains, P) copy of the parameters without `missing`, plus the mask
+# (draws, chains, P) view of the samples as a dense Array{T} plus the per-parameter `missing` mask.  Nothing is compacted:
+# parameters that contain `missing` are handed to the library as they are (filler zero(T)) together with a skip mask
+# (mcd_set_param_mask), which neither stages nor reads them and NaN-fills their outputs; `_unpack` maps those to `missing`
+# (src/ess_rhat.jl:382-385,519-523).  For a plain Array{Float64/Float32} without Missing the "copy" is a reshape.
 function _pack(x::AbstractArray{<:Union{Missing,Real}})
     T = _floattype(x)
     T <: Union{Float32,Float64} || (T = Float64)
     draws = size(x, 1)
     chains = ndims(x) > 1 ? size(x, 2) : 1
     x3 = reshape(x, draws, chains, :)
-    keep = [!any(ismissing, view(x3, :, :, p)) for p in axes(x3, 3)]
-    dense = Array{T}(undef, draws, chains, count(keep))
-    j = 0
-    for p in axes(x3, 3)
-        keep[p] || continue
-        j += 1
-        dense[:, :, j] .= view(x3, :, :, p)
+    if !(Missing <: eltype(x))
+        dense = x3 isa Array{T,3} ? x3 : Array{T,3}(x3)
+        return T, dense, nothing
     end
-    return T, dense, keep
+    skip = UInt8[any(ismissing, view(x3, :, :, p)) for p in axes(x3, 3)]
+    dense = Array{T,3}(undef, draws, chains, size(x3, 3))
+    @inbounds for i in eachindex(x3)
+        v = x3[i]
+        dense[i] = v === missing ? zero(T) : T(v)
+    end
+    return T, dense, skip
 end
 
-function _unpack(x, ::Type{T}, vals::Vector, keep) where {T}
+# hand the skip mask (if any) to the library: it is consumed by the next call on the context
+function _set_mask(skip)
+    (skip === nothing || !any(!iszero, skip)) && return nothing
+    GC.@preserve skip begin
+        rc = ccall((:mcd_set_param_mask, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), context(), skip, length(skip))
+        _check(rc)
+    end
+    return nothing
+end
+
+function _unpack(x, ::Type{T}, vals::Vector, skip) where {T}
     TM = Missing <: eltype(x) ? Union{Missing,T} : T
     out = similar(x, TM, _param_axes(x))
     lin = LinearIndices(out)
-    j = 0
-    for (p, k) in enumerate(keep)
-        if k
-            j += 1
-            out[lin[p]] = vals[j]
-        else
-            out[lin[p]] = missing
-        end
+    for p in eachindex(vals)
+        out[lin[p]] = (skip !== nothing && skip[p] != 0) ? missing : vals[p]
     end
     return _maybescalar(out)
 end
+
+_clamp_maxlag(maxlag::Integer) = Cint(clamp(maxlag, -1, typemax(Cint)))
 
 _tailprob(tp::Rational) = (Float64(tp), Cint(0))
 _tailprob(tp::Float32) = (Float64(tp), Cint(0))
@@ -117,8 +136,10 @@ _tailprob(tp::Real) = (Float64(tp), Cint(1))
 function _ess_rhat_call(x, kind::Symbol, want_ess::Bool, want_rhat::Bool; relative::Bool=false,
                         autocov_method::AbstractAutocovMethod=AutocovMethod(), split_chains::Int=2,
                         maxlag::Int=250, tail_prob::Real=1//10)
+    if eltype(x) === Missing   # nothing but `missing`: no float type to compute in (checked before `_pack`)
+        return (want_ess ? similar(x, Missing, _param_axes(x)) : nothing, want_rhat ? similar(x, Missing, _param_axes(x)) : nothing)
+    end
     T, dense, keep = _pack(x)
-    all(ismissing, x) && eltype(x) === Missing && return (similar(x, Missing, _param_axes(x)), similar(x, Missing, _param_axes(x)))
     niter = size(dense, 1) ÷ split_chains
     if want_ess
         if !(niter > 4)
@@ -131,12 +152,13 @@ function _ess_rhat_call(x, kind::Symbol, want_ess::Bool, want_rhat::Bool; relati
     S = Vector{T}(undef, want_ess ? P : 0)
     R = Vector{T}(undef, want_rhat ? P : 0)
     tp, tp64 = _tailprob(tail_prob)
+    _set_mask(keep)
     GC.@preserve dense S R begin
         rc = ccall((:mcd_ess_rhat, LIB), Cint,
                    (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Cint, Cint, Cint, Cint, Cint, Cdouble, Cint,
                     Ptr{Cvoid}, Ptr{Cvoid}),
                    context(), dense, MCD_HOST, _dtype(T), size(dense, 1), size(dense, 2), P, KIND[kind],
-                   _code(autocov_method), split_chains, clamp(maxlag, -1, typemax(Cint)), relative, tp, tp64,
+                   _code(autocov_method), split_chains, _clamp_maxlag(maxlag), relative, tp, tp64,
                    want_ess ? pointer(S) : C_NULL, want_rhat ? pointer(R) : C_NULL)
         _check(rc, maxlag)
     end
@@ -166,17 +188,18 @@ function _estimator_call(fname::Symbol, x, est; relative::Bool=false, autocov_me
     end
     P = size(dense, 3)
     out = Vector{T}(undef, P)
+    _set_mask(keep)
     GC.@preserve dense out begin
         rc = if fname === :mcd_mcse
             ccall((:mcd_mcse, LIB), Cint,
                   (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Cint, Cdouble, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
                   context(), dense, MCD_HOST, _dtype(T), size(dense, 1), size(dense, 2), P, code, p, p64,
-                  _code(autocov_method), split_chains, maxlag, out)
+                  _code(autocov_method), split_chains, _clamp_maxlag(maxlag), out)
         else
             ccall((:mcd_ess_estimator, LIB), Cint,
                   (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Cint, Cdouble, Cint, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
                   context(), dense, MCD_HOST, _dtype(T), size(dense, 1), size(dense, 2), P, code, p, p64,
-                  _code(autocov_method), split_chains, maxlag, relative, out)
+                  _code(autocov_method), split_chains, _clamp_maxlag(maxlag), relative, out)
         end
         _check(rc, maxlag)
     end
@@ -213,14 +236,29 @@ function ess_rhat(samples::AbstractArray{<:Union{Missing,Real}}; kind::Symbol=:r
     return (; ess=S, rhat=R)
 end
 
-"""`mcse(samples; kind=Statistics.mean, kwargs...)` (src/mcse.jl:5-42).  mean / std / median / quantile run on the
-GPU; every other estimator uses the reference's subsampling bootstrap, which needs a Julia closure per window and
-therefore stays in the reference package (SURVEY.md §2: out of scope)."""
+"""`mcse(samples; kind=Statistics.mean, kwargs...)` (src/mcse.jl:5-42).  mean / std / median / quantile run on the GPU
+(the ESS-based rules, src/mcse.jl:45-118).  Every other estimator takes the reference's subsampling-bootstrap fallback
+`_mcse_sbm(f, x; batch_size)` (src/mcse.jl:120-148), which evaluates a Julia closure per batch: it is host logic in the
+reference and stays host logic here, by delegating to the loaded MCMCDiagnosticTools package (the drop-in keeps the
+reference's own code for it, SURVEY.md §2)."""
 function mcse(samples::AbstractArray{<:Union{Missing,Real}}; kind=Statistics.mean, kwargs...)
     est = _estimator(kind)
-    (est === nothing || est[1] == 3) &&
-        throw(ArgumentError("mcse for $kind uses the subsampling bootstrap of MCMCDiagnosticTools (src/mcse.jl:120-148)"))
-    return _estimator_call(:mcd_mcse, samples, est; kwargs...)
+    if est === nothing || est[1] == 3
+        f = kind isa Symbol ? StatsBase.mad : kind
+        return _reference_mcse_sbm(f, samples; kwargs...)
+    end
+    haskey(kwargs, :relative) && kwargs[:relative] &&
+        throw(ArgumentError("mcse(...; relative=true) is not supported by the accelerated path"))
+    return _estimator_call(:mcd_mcse, samples, est; (k => v for (k, v) in kwargs if k !== :relative)...)
+end
+
+# `_mcse_sbm` of the reference package itself (found among the loaded modules: the shim does not depend on it)
+function _reference_mcse_sbm(f, samples; kwargs...)
+    id = Base.PkgId(Base.UUID("be115224-59cd-429b-ad48-344e309966f0"), "MCMCDiagnosticTools")
+    pkg = get(Base.loaded_modules, id, nothing)
+    pkg === nothing && throw(ArgumentError(
+        "mcse for $f uses the subsampling bootstrap of MCMCDiagnosticTools (src/mcse.jl:120-148): load MCMCDiagnosticTools next to this shim"))
+    return pkg._mcse_sbm(f, samples; kwargs...)
 end
 
 const SUMMARY_FIELDS = (:mean, :std, :mcse_mean, :mcse_std, :ess_bulk, :ess_tail, :rhat)
@@ -245,11 +283,12 @@ function summary_columns(samples::AbstractArray{<:Union{Missing,Real}}; fields=S
     P = size(dense, 3)
     out = Matrix{T}(undef, P, length(names))
     tp, tp64 = _tailprob(tail_prob)
+    _set_mask(keep)
     GC.@preserve dense out begin
         rc = ccall((:mcd_summary, LIB), Cint,
                    (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Cuint, Cint, Cint, Cint, Cdouble, Cint, Ptr{Cvoid}),
                    context(), dense, MCD_HOST, _dtype(T), size(dense, 1), size(dense, 2), P, mask,
-                   _code(autocov_method), split_chains, maxlag, tp, tp64, out)
+                   _code(autocov_method), split_chains, _clamp_maxlag(maxlag), tp, tp64, out)
         _check(rc, maxlag)
     end
     return NamedTuple{names}(Tuple(_unpack(samples, T, out[:, i], keep) for i in eachindex(names)))
@@ -278,6 +317,7 @@ function rhat_nested(samples::AbstractArray{<:Union{Missing,Real}}, superchain_i
     T, dense, keep = _pack(samples)
     P = size(dense, 3)
     out = Vector{T}(undef, P)
+    _set_mask(keep)
     GC.@preserve dense out inds begin
         rc = ccall((:mcd_rhat_nested, LIB), Cint,
                    (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Ptr{Int32}, Int64, Int64, Cint, Cint, Ptr{Cvoid}),
@@ -289,57 +329,9 @@ function rhat_nested(samples::AbstractArray{<:Union{Missing,Real}}, superchain_i
 end
 
 
-# ---- in-package callers of the path (src/gewekediag.jl:19-35, src/heideldiag.jl:16-71): unchanged host logic,
-# their two `mcse(...; split_chains=1)` calls land on the device through `mcse` above --------------------------
-function gewekediag(x::AbstractVector{<:Real}; first::Real=0.1, last::Real=0.5, kwargs...)
-    0 < first < 1 || throw(ArgumentError("`first` is not in (0, 1)"))
-    0 < last < 1 || throw(ArgumentError("`last` is not in (0, 1)"))
-    first + last <= 1 || throw(ArgumentError("`first` and `last` proportions overlap"))
-    n = length(x)
-    x1 = x[1:round(Int, first * n)]
-    x2 = x[round(Int, n - last * n + 1):n]
-    s = hypot(Base.first(mcse(reshape(x1, :, 1, 1); split_chains=1, kwargs...)),
-              Base.first(mcse(reshape(x2, :, 1, 1); split_chains=1, kwargs...)))
-    z = (Statistics.mean(x1) - Statistics.mean(x2)) / s
-    return (zscore=z, pvalue=SpecialFunctions.erfc(abs(z) / sqrt(2)))
-end
-
-function heideldiag(x::AbstractVector{<:Real}; alpha::Real=1//20, eps::Real=0.1, start::Int=1, kwargs...)
-    n = length(x)
-    delta = trunc(Int, 0.10 * n)
-    y = x[trunc(Int, n / 2):end]
-    T = typeof(zero(eltype(x)) / 1)
-    s = Base.first(mcse(reshape(y, :, 1, 1); split_chains=1, kwargs...))
-    S0 = length(y) * s^2
-    i, pvalue, converged, ybar = 1, one(T), false, T(NaN)
-    while i < n / 2
-        y = x[i:end]
-        m = length(y)
-        ybar = Statistics.mean(y)
-        B = cumsum(y) - ybar * collect(1:m)
-        I = sum((B .* B) ./ (m * S0)) / m
-        pvalue = 1 - T(_pcramer(I))
-        converged = pvalue > alpha
-        converged && break
-        i += delta
-    end
-    s = Base.first(mcse(reshape(y, :, 1, 1); split_chains=1, kwargs...))
-    halfwidth = sqrt(2) * SpecialFunctions.erfcinv(T(alpha)) * s
-    return (burnin=i + start - 2, stationarity=converged, pvalue=pvalue, mean=ybar, halfwidth=halfwidth,
-            test=halfwidth / abs(ybar) <= eps)
-end
-
-# Csorgo & Faraway (1996) series for the Cramer-von Mises distribution
-function _pcramer(q::Real)
-    p = 0.0
-    for k in 0:3
-        c1 = 4.0 * k + 1.0
-        c2 = c1^2 / (16.0 * q)
-        p += SpecialFunctions.gamma(k + 0.5) / factorial(k) * sqrt(c1) * exp(-c2) * SpecialFunctions.besselk(0.25, c2)
-    end
-    return p / (pi^1.5 * sqrt(q))
-end
-
+# (`gewekediag` and `heideldiag`, src/gewekediag.jl:19-35 / src/heideldiag.jl:16-71, are NOT redefined here: they live outside the
+# C boundary, and the package's own definitions reach the device unchanged through the `mcse` above once it is the
+# `mcse` in scope -- see INTEGRATION.md.)
 
 # ---- SURVEY §8(f)4: moment kernels behind a different combine ----------------------------------------------
 """`bfmi(energy; dims=1)` (src/bfmi.jl:36-43) on the device: one value per chain."""
