@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libmcmcdiag_b200.so")
 COMMON = ["mcd_common.cuh", "mcd_slab.cuh", "mcd_fast.cuh", "mcd_rk2_api.cuh", "mcd_big_api.cuh"]
 # translation unit -> headers it depends on (besides COMMON and the public header)
 UNITS = {
-    "mcd_api.cu": ["mcd_fastgen.cuh", "mcd_large.cuh"],
+    "mcd_api.cu": ["mcd_fastgen.cuh", "mcd_large.cuh", "mcd_crank.cuh"],
     "mcd_rk2.cu": ["mcd_rk2.cuh", "mcd_tma.cuh"],
     "mcd_big.cu": ["mcd_big.cuh", "mcd_big_api.cuh", "mcd_tma.cuh"],
 }

@@ -59,7 +59,11 @@ struct mcd_ctx {
   int fast_grid_mult = 0;  // developer knob: 0 = one CTA per parameter, k = persistent grid of k * 2 * SMs CTAs
   int use_rk2 = 1;         // developer knob: 0 = round-1 register-resident kernel instead of the TMA-staged one
   int use_big = 1;         // developer knob: 0 = never use the big-slab estimator kernel (mcd_big.cuh)
+  int use_crank = 1;       // developer knob: 0 = large slabs are always ranked by segmented sort + binary searches
+  int crank_factor = 4;    // counting rank: fine buckets per value
+  long long crank_chunk = 0;   // counting rank: cap on the parameters per chunk (0 = workspace-bound)
   // stats
+  long long crank_chunks = 0, crank_fallbacks = 0;
   long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   int last_path = 0;
 };
@@ -725,6 +729,14 @@ static int run_device(mcd_ctx* ctx, const T* dx, long long params, const SplitGe
   env.work = &ctx->work; env.work_cap = &ctx->work_cap; env.smem_optin = ctx->smem_optin;
   env.d_chain_inds = ctx->d_chain_inds;
   env.rel_ess_max = (double)rel_ess_max_of<T>((long long)g.niter * g.nch);
+  env.use_crank = ctx->use_crank; env.crank_factor = ctx->crank_factor; env.crank_chunk = ctx->crank_chunk;
+  env.crank_chunks = &ctx->crank_chunks; env.crank_fallbacks = &ctx->crank_fallbacks;
+  // the counting rank turns ranks into z by a table lookup while the table stays cache-sized (<= 32 MB)
+  if (ctx->use_crank && g.n >= 1024 && (size_t)g.n * 4 * sizeof(T) <= ((size_t)32 << 20)) {
+    const int zrc = ensure_ztab(ctx, sizeof(T) == 8 ? MCD_F64 : MCD_F32, g.n);
+    if (zrc) return zrc;
+    env.ztab = ctx->ztab;
+  }
   std::string msg;
   int rc = run_large<T>(env, dx, params, g, pg.nsteps, pg.steps, pg.combine, pg.method, pg.maxlag, pg.relative,
                         pg.ess_nan, pg.mcse_p, (int)pg.cps, (int)pg.nsuper, d_ess, d_rhat, d_arr, msg);
@@ -1232,6 +1244,9 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   else if (k == "fast_grid_mult") { ctx->fast_grid_mult = (int)value; }
   else if (k == "use_rk2") { ctx->use_rk2 = (int)value; }
   else if (k == "use_big") { ctx->use_big = (int)value; }
+  else if (k == "use_crank") { ctx->use_crank = (int)value; }
+  else if (k == "crank_factor") { if (value < 1 || value > 64) return fail(ctx, MCD_EINVAL, "crank_factor in 1..64"); ctx->crank_factor = (int)value; }
+  else if (k == "crank_chunk") { if (value < 0) return fail(ctx, MCD_EINVAL, "crank_chunk >= 0"); ctx->crank_chunk = value; }
   else if (k == "slab_wide") ctx->slab_wide = value ? 1 : 0;
   else if (k == "sort_bucket_limit") { if (value < 0) return fail(ctx, MCD_EINVAL, "sort_bucket_limit >= 0"); ctx->bucket_limit = (int)value; }
   else return fail(ctx, MCD_EINVAL, "unknown option '%s'", key);
@@ -1251,6 +1266,8 @@ int64_t mcd_get_stat(const mcd_ctx* ctx, const char* key) {
     return mcd_get_stat(ctx->children[0], key);
   }
   if (k == "kernel_launches") return ctx->launches;
+  if (k == "crank_chunks") return ctx->crank_chunks;        // chunks of large slabs ranked by counting (cumulative)
+  if (k == "crank_fallbacks") return ctx->crank_fallbacks;  // counting-rank attempts handed to the sort path (cumulative)
   if (k == "last_path") return ctx->last_path;
   if (k == "h2d_bytes") return ctx->h2d_bytes;
   if (k == "d2h_bytes") return ctx->d2h_bytes;

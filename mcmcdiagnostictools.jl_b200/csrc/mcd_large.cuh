@@ -13,6 +13,7 @@
 #pragma once
 #include "mcd_common.cuh"
 #include "mcd_slab.cuh"
+#include "mcd_crank.cuh"
 #include <algorithm>
 #include <string>
 
@@ -29,6 +30,12 @@ struct LargeEnv {
   size_t* work_cap;
   const int* d_chain_inds;
   double rel_ess_max;
+  int use_crank = 1;          // counting rank (mcd_crank.cuh) instead of segmented sort + binary searches where it applies
+  int crank_factor = 4;       // fine buckets per value (rounded up to a power of two)
+  long long crank_chunk = 0;  // cap on the parameters per chunk on the counting-rank path (0 = workspace-bound)
+  long long* crank_chunks = nullptr;     // statistics: chunks ranked by counting / sent to the sort path
+  long long* crank_fallbacks = nullptr;
+  const void* ztab = nullptr;            // z for the doubled rank r2 at [r2 - 2] (ztab_kernel), or null: evaluate per element
 };
 
 constexpr int LG_THREADS = 256;
@@ -140,6 +147,22 @@ __global__ void __launch_bounds__(LG_THREADS) rank_kernel(const T* __restrict__ 
     const long long r2 = lb + ub + 1;
     if (ranks_out) ranks_out[gid] = 0.5 * (double)r2;
     else Yout[gid] = z_from_rank2<T>(r2, n);
+  }
+}
+
+// counting-rank variant (mcd_crank.cuh): the doubled rank comes from the bucket structure
+template <typename T>
+__global__ void __launch_bounds__(CR_THREADS) crank_rank_kernel(CrWork<T> w, long long n, T* __restrict__ Yout,
+                                                                double* __restrict__ ranks_out,
+                                                                const T* __restrict__ ztab) {
+  const long long p = blockIdx.y;
+  if (w.flag[p]) return;
+  const long long t0 = (long long)blockIdx.x * CR_TILE;
+  const long long t1 = t0 + CR_TILE < n ? t0 + CR_TILE : n;
+  for (long long i = t0 + threadIdx.x; i < t1; i += CR_THREADS) {
+    const long long r2 = cr_rank_body<T>(w, n, p, i);
+    if (ranks_out) ranks_out[p * n + i] = 0.5 * (double)r2;
+    else Yout[p * n + i] = ztab ? __ldg(&ztab[r2 - 2]) : z_from_rank2<T>(r2, n);   // ztab[r2 - 2] = z_from_rank2(r2, n)
   }
 }
 
@@ -732,6 +755,16 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   }
   const long long nan_tiles = (n + NAN_TILE - 1) / NAN_TILE;
   const long long gam_stride = maxlag + 1 + LAG_BATCH;
+  // counting rank: every use of the sorted copy must be one it provides (ranks, median)
+  bool crankable = env.use_crank && needs_sort && combine != CB_MCSE_QUANTILE && n >= 1024 && n <= (long long)CR_MAX_N;
+  for (int s = 0; s < nsteps; ++s) {
+    const int tr = steps[s].transform;
+    crankable &= tr == TR_NONE || tr == TR_STDPROXY || tr == TR_RANKNORM || tr == TR_TIEDRANK || tr == TR_FOLD ||
+                 tr == TR_FOLD_RANKNORM;
+  }
+  unsigned cr_buckets = 1u << 16;
+  while ((long long)cr_buckets < (long long)std::max(1, env.crank_factor) * n && cr_buckets < (1u << 28)) cr_buckets <<= 1;
+  const long long cr_nw = cr_buckets / 8;
 
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
   // bytes per parameter of workspace
@@ -744,8 +777,13 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   if (fft_big) per += al((size_t)g.nch * fftN * 2 * ts);
   if (any_nested) per += al((size_t)2 * nsuper * 8);
   per += 256 * 2;  // thresholds, nnan, results (per-param scalars; generous)
+  if (crankable) per += al((size_t)cr_nw * 8) + al((size_t)CR_NSEG * 4) + 64;
   long long chunk = std::max<long long>(1, env.workspace_bytes / (long long)per);
   chunk = std::min(chunk, params);
+  if (crankable) {
+    chunk = std::min<long long>(chunk, 65535);   // grid.y of the counting-rank kernels
+    if (env.crank_chunk > 0) chunk = std::min(chunk, env.crank_chunk);
+  }
   // grid limits: blocks = chunk * tiles must stay below 2^31
   const long long sort_tiles = (n + SORT_TILE - 1) / SORT_TILE, merge_tiles = (n + MERGE_TILE - 1) / MERGE_TILE;
   const long long max_tiles = std::max<long long>(std::max(sort_tiles, merge_tiles), std::max<long long>(nan_tiles, g.nch));
@@ -768,6 +806,9 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   const size_t oFB = carve(fft_big ? (size_t)chunk * g.nch * fftN * 2 * ts : 0);
   const size_t oTHR = carve(scal), oTHR2 = carve(scal), oEX0 = carve(scal), oEX1 = carve(scal);
   const size_t oNNX = carve(scal), oNNY = carve(scal);
+  const size_t oCRW = carve(crankable ? (size_t)chunk * cr_nw * 8 : 0);
+  const size_t oCRP = carve(crankable ? (size_t)chunk * CR_NSEG * 4 : 0);
+  const size_t oCRK0 = carve(scal), oCRK1 = carve(scal), oCRM = carve(2 * scal), oCRF = carve(scal + 256);
   size_t oRE[MAX_STEPS], oRR[MAX_STEPS];
   for (int s = 0; s < MAX_STEPS; ++s) { oRE[s] = carve(scal); oRR[s] = carve(scal); }
   (void)scal;
@@ -849,6 +890,39 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
       if (sortedX) return 0;
       return seg_sort(X, nnX, &sortedX);
     };
+    // counting rank of V (pc segments of n): 1 = done (Yout / ranks_out written when do_rank; the structures stay
+    // valid for crank_median_kernel until the next call), 0 = a slab of the chunk needs the sort path, < 0 = error
+    CrWork<T> cw;
+    cw.kmin = (typename CrKeyOf<T>::type*)(wb + oCRK0); cw.kmax = (typename CrKeyOf<T>::type*)(wb + oCRK1);
+    cw.map = (CrMap<T>*)(wb + oCRM); cw.flag = (int*)(wb + oCRF); cw.cw = (uint2*)(wb + oCRW);
+    cw.part = (unsigned*)(wb + oCRP); cw.info = (unsigned*)SB; cw.srt = (T*)SA;
+    cw.nw = cr_nw; cw.buckets = cr_buckets; cw.seg = (cr_nw + CR_NSEG - 1) / CR_NSEG;
+    auto crank = [&](const T* V, T* Yout, double* ranks_out, bool do_rank) -> int {
+      using CK = typename CrKeyOf<T>::type;
+      LCU(cudaMemsetAsync(cw.kmin, 0xff, (size_t)pc * sizeof(CK), st));
+      LCU(cudaMemsetAsync(cw.kmax, 0, (size_t)pc * sizeof(CK), st));
+      LCU(cudaMemsetAsync(cw.flag, 0, (size_t)(pc + 1) * sizeof(int), st));
+      LCU(cudaMemsetAsync(cw.cw, 0, (size_t)pc * cr_nw * 8, st));
+      const dim3 grid((unsigned)((n + CR_TILE - 1) / CR_TILE), (unsigned)pc);
+      const unsigned pb = (unsigned)((pc + 127) / 128);
+      crank_minmax_kernel<T><<<grid, CR_THREADS, 0, st>>>(cw, V, n); LAUNCHED();
+      crank_setup_kernel<T><<<pb, 128, 0, st>>>(cw, pc); LAUNCHED();
+      crank_count_kernel<T><<<grid, CR_THREADS, 0, st>>>(cw, V, n); LAUNCHED();
+      const unsigned sb = (unsigned)((pc * CR_NSEG * 32 + CR_THREADS - 1) / CR_THREADS);
+      crank_scan1_kernel<T><<<sb, CR_THREADS, 0, st>>>(cw, pc); LAUNCHED();
+      crank_scan3_kernel<T><<<sb, CR_THREADS, 0, st>>>(cw, pc); LAUNCHED();
+      crank_anyflag_kernel<T><<<pb, 128, 0, st>>>(cw, pc); LAUNCHED();
+      int any = 0;
+      LCU(cudaMemcpyAsync(&any, cw.flag + pc, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LCU(cudaStreamSynchronize(st));
+      if (any) { if (env.crank_fallbacks) ++*env.crank_fallbacks; return 0; }
+      crank_place_kernel<T><<<grid, CR_THREADS, 0, st>>>(cw, V, n); LAUNCHED();
+      if (do_rank) { crank_rank_kernel<T><<<grid, CR_THREADS, 0, st>>>(cw, n, Yout, ranks_out, (const T*)env.ztab); LAUNCHED(); }
+      if (env.crank_chunks) ++*env.crank_chunks;
+      return 1;
+    };
+    bool crankX = false;            // the counting structures describe X
+    bool sortX = !crankable;        // X goes (or went) through the sort path
     const unsigned pblocks = (unsigned)((pc + 127) / 128);
 
     for (int s = 0; s < nsteps; ++s) {
@@ -857,25 +931,49 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
       int rc = 0;
       switch (stp.transform) {
         case TR_NONE: break;
-        case TR_RANKNORM:
+        case TR_RANKNORM: case TR_TIEDRANK: {
+          T* yo = stp.transform == TR_RANKNORM ? Y : nullptr;
+          double* ro = stp.transform == TR_RANKNORM ? nullptr : (double*)d_arr + done * n;
+          if (stp.transform == TR_RANKNORM) proxy = Y;
+          if (!sortX) {
+            const int cr = crank(X, yo, ro, true);
+            if (cr < 0) return cr;
+            if (cr == 1) { crankX = true; break; }
+            sortX = true;
+          }
+          crankX = false;
           if ((rc = ensure_sortedX())) return rc;
-          if ((rc = rank_of(X, sortedX, nnX, Y, nullptr))) return rc;
-          proxy = Y;
+          if ((rc = rank_of(X, sortedX, nnX, yo, ro))) return rc;
           break;
-        case TR_TIEDRANK:
-          if ((rc = ensure_sortedX())) return rc;
-          if ((rc = rank_of(X, sortedX, nnX, nullptr, (double*)d_arr + done * n))) return rc;
-          break;
+        }
         case TR_FOLD: case TR_FOLD_RANKNORM: case TR_FOLD_IND_MEDIAN: {
-          if ((rc = ensure_sortedX())) return rc;
-          select_kernel<T><<<pblocks, 128, 0, st>>>(sortedX, nnX, n, pc, SEL_MEDIAN, 0.0, 0, thr, nullptr);
-          LAUNCHED();
+          if (!sortX && !crankX) {
+            const int cr = crank(X, nullptr, nullptr, false);
+            if (cr < 0) return cr;
+            if (cr == 1) crankX = true; else sortX = true;
+          }
+          if (crankX) {
+            crank_median_kernel<T><<<pblocks, 128, 0, st>>>(cw, n, pc, thr);
+            LAUNCHED();
+          } else {
+            if ((rc = ensure_sortedX())) return rc;
+            select_kernel<T><<<pblocks, 128, 0, st>>>(sortedX, nnX, n, pc, SEL_MEDIAN, 0.0, 0, thr, nullptr);
+            LAUNCHED();
+          }
           elementwise_kernel<T><<<ew_blocks, LG_THREADS, 0, st>>>(X, Y, thr, n, total, EW_FOLD);
           LAUNCHED();
           proxy = Y;
           if (stp.transform == TR_FOLD) break;
+          if (crankable && stp.transform == TR_FOLD_RANKNORM) {
+            crankX = false;       // the counting structures (and the sort buffers under them) are about to be reused
+            sortedX = nullptr;
+            const int cr = crank(Y, Y, nullptr, true);
+            if (cr < 0) return cr;
+            if (cr == 1) break;
+          }
           const Key* sortedY = nullptr;
           sortedX = nullptr;  // the sort buffers are about to be reused
+          crankX = false;
           if ((rc = seg_sort(Y, nnY, &sortedY))) return rc;
           if (stp.transform == TR_FOLD_RANKNORM) {
             if ((rc = rank_of(Y, sortedY, nnY, Y, nullptr))) return rc;

@@ -29,6 +29,12 @@
 #include "mcd_rk2_api.cuh"
 #include "mcd_tma.cuh"
 
+// developer switch (A/B builds): 1 = the merge loop keeps one value of lookahead per run in registers (same-box A/B:
+// 11.30 ms per 200 k parameters with it, 11.26 without: fewer selects win once every warp of the SM merges at once)
+#ifndef RK_MERGE_LOOKAHEAD
+#define RK_MERGE_LOOKAHEAD 0
+#endif
+
 namespace mcd {
 
 constexpr int RK_THREADS = 256;
@@ -60,7 +66,7 @@ constexpr int RK_A_FR = RK_WORDS * 4 + RK_WORDS * 2 - (RK_NMAX + 32) * 2;   // e
 constexpr int RK_A_RHO = RK_NCH * RK_ROW * 8;
 constexpr int RK_A_PART = RK_A_BYTES - RK_NCH * RK_LAGS * 8;
 constexpr int RK_OFF_SMALL = RK_OFF_A + RK_A_BYTES;
-constexpr int RK_SMALL_BYTES = 512;
+constexpr int RK_SMALL_BYTES = 640;
 constexpr int RK_SMEM_BYTES = RK_OFF_SMALL + RK_SMALL_BYTES;
 static_assert(RK_A_FR >= RK_NCH * RK_ROW * 8, "FR must not overlap the centred rows");
 static_assert((RK_A_PART - RK_A_RHO) / 8 - (RK_LAGS + 1) >= RK_MAXLAG_CAP && RK_MAXLAG_CAP >= RK_MAXITER, "rho[] must hold every admissible maxlag");
@@ -69,6 +75,28 @@ static_assert(RK_SEG * RK_THREADS >= RK_NMAX, "every merged value needs a thread
 template <typename T> __device__ __forceinline__ T rk_inf();
 template <> __device__ __forceinline__ double rk_inf<double>() { return CUDART_INF; }
 template <> __device__ __forceinline__ float rk_inf<float>() { return CUDART_INF_F; }
+
+
+// Order-preserving integer key of a value's leading 32 bits (for double: the high word, i.e. sign, exponent and
+// 20 mantissa bits; for float: the whole value).  key(a) < key(b) implies a < b, so the minimum / maximum KEY of
+// a slab bounds its range from below / above by less than one unit of those 20 bits: all the bucket map needs.
+// Integer min / max are one VIMNMX3 per two values and one REDUX per warp (FP64 min / max: DSETP + 2 FSEL per
+// value and ten shuffles per warp).  NaN and +-Inf have keys beyond the finite range (they go to the redo list).
+template <typename T> struct RkKey;
+template <> struct RkKey<double> {
+  static constexpr bool exact = false;
+  static constexpr int pos_inf = 0x7ff00000, neg_inf = (int)0x800fffffu;
+  static __device__ __forceinline__ int key(double v) { const int h = __double2hiint(v); return h ^ ((h >> 31) & 0x7fffffff); }
+  static __device__ __forceinline__ double lower(int k) { const int h = k ^ ((k >> 31) & 0x7fffffff); return __hiloint2double(h, h < 0 ? -1 : 0); }
+  static __device__ __forceinline__ double upper(int k) { const int h = k ^ ((k >> 31) & 0x7fffffff); return __hiloint2double(h, h < 0 ? 0 : -1); }
+};
+template <> struct RkKey<float> {
+  static constexpr bool exact = true;
+  static constexpr int pos_inf = 0x7f800000, neg_inf = (int)0x807fffffu;
+  static __device__ __forceinline__ int key(float v) { const int h = __float_as_int(v); return h ^ ((h >> 31) & 0x7fffffff); }
+  static __device__ __forceinline__ float lower(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+  static __device__ __forceinline__ float upper(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+};
 
 // LONG = every split chain has more than 480 draws: only the last of a thread's 16 slots can be empty.
 // sums of the eight 4-bit fields of each of the four words of c, as prefix pieces:
@@ -111,6 +139,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a)
   unsigned* listlen = reinterpret_cast<unsigned*>(small + 416);
   int* decision = reinterpret_cast<int*>(small + 420);
   unsigned long long* mbar_ptr = reinterpret_cast<unsigned long long*>(small + 448);
+  int* ikey = reinterpret_cast<int*>(small + 512);          // [2][8]  per-warp min / max keys
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const bool last_live = lane + 32 * (RK_EPT - 1) < niter;
@@ -167,14 +196,34 @@ __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a)
         // clear the packed counters: the barrier of the min / max exchange covers it
         for (int i = tid; i < RK_WORDS / 4; i += RK_THREADS) reinterpret_cast<uint4*>(FC)[i] = make_uint4(0, 0, 0, 0);
         T vmin, vmax;
+        bool exact_minmax = false;
         {
+          int kmin = 0x7fffffff, kmax = (int)0x80000000u;
+#pragma unroll
+          for (int k = 0; k < RK_EPT; ++k) {
+            const int key = RkKey<T>::key(x[k]);
+            kmin = min(kmin, live(k) ? key : 0x7fffffff);
+            kmax = max(kmax, live(k) ? key : (int)0x80000000u);
+          }
+          kmin = __reduce_min_sync(0xffffffffu, kmin);
+          kmax = __reduce_max_sync(0xffffffffu, kmax);
+          if (lane == 0) { ikey[w] = kmin; ikey[8 + w] = kmax; }
+          __syncthreads();   // also: every thread holds its x in registers, XS is free to become S
+          kmin = ikey[0]; kmax = ikey[8];
+#pragma unroll
+          for (int i = 1; i < RK_NCH; ++i) { kmin = min(kmin, ikey[i]); kmax = max(kmax, ikey[8 + i]); }
+          if (kmax >= RkKey<T>::pos_inf || kmin <= RkKey<T>::neg_inf) { redo = true; break; }   // NaN or +-Inf
+          // fewer than 64 key steps between the extremes: the key bounds would widen the range noticeably (or the
+          // slab is constant): take the exact minimum and maximum instead
+          exact_minmax = !RkKey<T>::exact && (long long)kmax - (long long)kmin < 64;
+          vmin = RkKey<T>::lower(kmin); vmax = RkKey<T>::upper(kmax);
+        }
+        if (exact_minmax) {
           T lmin = rk_inf<T>(), lmax = -rk_inf<T>();
-          int bad = 0;
 #pragma unroll
           for (int k = 0; k < RK_EPT; ++k) {
             if (live(k)) {
               const T v = x[k];
-              bad |= (v != v);
               lmin = v < lmin ? v : lmin;
               lmax = v > lmax ? v : lmax;
             }
@@ -184,18 +233,14 @@ __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a)
             const T p = __shfl_xor_sync(0xffffffffu, lmin, o); lmin = p < lmin ? p : lmin;
             const T q = __shfl_xor_sync(0xffffffffu, lmax, o); lmax = q > lmax ? q : lmax;
           }
-          bad = __any_sync(0xffffffffu, bad);
-          if (lane == 0) { wred[w] = (double)lmin; wred[8 + w] = (double)lmax; iflag[w] = bad; }
-          __syncthreads();   // also: every thread holds its x in registers, XS is free to become S
+          if (lane == 0) { wred[w] = (double)lmin; wred[8 + w] = (double)lmax; }
+          __syncthreads();
           vmin = (T)wred[0]; vmax = (T)wred[8];
-          int anybad = iflag[0];
 #pragma unroll
           for (int i = 1; i < RK_NCH; ++i) {
             const T p = (T)wred[i], q = (T)wred[8 + i];
             vmin = p < vmin ? p : vmin; vmax = q > vmax ? q : vmax;
-            anybad |= iflag[i];
           }
-          if (anybad) { redo = true; break; }
         }
         flat = !(vmax > vmin);
         const T range = vmax - vmin;
@@ -204,7 +249,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a)
         if (!flat && (!(range < rk_inf<T>()) || !(scale > (T)0) || !(scale < rk_inf<T>()))) { redo = true; break; }
         if (flat) {
           zflat = __ldg(&a.ztab[((n - 1) >> 1) + (((n - 1) & 1) ? n : 0)]);   // every value ties: rank (n+1)/2
-          __syncthreads();   // iflag / wred reads done before anything below reuses them
+          __syncthreads();   // wred reads done before anything below reuses the small arrays
           prefetch_next();
         } else {
           // ---- count: 4-bit packed populations, ONE shared-memory atomic per element; it returns the arrival offset ----
@@ -373,13 +418,12 @@ __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a)
       const bool do_ess = BULK && a.want_ess && !a.ess_nan;
       bool rows_written = false;
       auto write_rows = [&]() {
-        double* row = ZC + w * RK_ROW;
+        // t = lane + 32 k sits at t + (t >> 4) = (lane + (lane >> 4)) + 34 k: one base, compile-time offsets
+        double* rp = ZC + w * RK_ROW + lane + (lane >> 4);
 #pragma unroll
-        for (int k = 0; k < RK_EPT; ++k) {
-          const int t = lane + 32 * k;
-          row[t + (t >> 4)] = (double)z[k];
-        }
-        for (int t = RK_MAXITER + lane; t < RK_TMAX; t += 32) row[t + (t >> 4)] = 0.0;
+        for (int k = 0; k < RK_EPT; ++k) rp[34 * k] = (double)z[k];
+#pragma unroll
+        for (int k = RK_EPT; k < RK_TMAX / 32; ++k) rp[34 * k] = 0.0;   // zero fill of [RK_MAXITER, RK_TMAX)
         rows_written = true;
       };
 
@@ -420,7 +464,9 @@ __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a)
             if (lo > 0) { prev = S[pa + 1] - med; has_prev = true; }
             if (m0 - lo > 0) { const T t = S[pb - 1] - med; if (!has_prev || fabs(t) > fabs(prev)) prev = t; has_prev = true; }
             T da = S[pa] - med, db = S[pb] - med;
+#if RK_MERGE_LOOKAHEAD
             T da2 = S[pa - 1] - med, db2 = S[pb + 1] - med;   // one value of lookahead per run: the load of a step is not on its critical path
+#endif
             if (!has_prev) prev = rk_inf<T>();   // |prev| = inf never equals a merged value of this segment (data are finite)
 #pragma unroll
             for (int i = 0; i < RK_SEG; ++i) {
@@ -432,9 +478,15 @@ __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a)
               const T f = takeA ? da : db;
               if (fabs(f) == fabs(prev)) tiebits |= 1u << i;
               prev = f;
+#if RK_MERGE_LOOKAHEAD
               if (takeA) { --pa; da = da2; } else { ++pb; db = db2; }
               const T d = S[takeA ? pa - 1 : pb + 1] - med;
               if (takeA) da2 = d; else db2 = d;
+#else
+              if (takeA) --pa; else ++pb;
+              const T d = S[takeA ? pa : pb] - med;
+              if (takeA) da = d; else db = d;
+#endif
             }
             const int cnt = n - m0 < RK_SEG ? n - m0 : RK_SEG;
             tiebits &= (cnt >= 32 ? 0xffffffffu : (1u << cnt) - 1u);

@@ -69,7 +69,15 @@ for dt in ("float64", "float32"):
     mild = torch.round(base * 300.0) / 300.0           # mild ties
     skew = torch.exp(base * 1.5)                       # lognormal: crowded buckets near zero
     const = torch.ones_like(base); const[:5] = base[:5]
-    for nm, xs in (("disc", disc), ("mild", mild), ("skew", skew), ("const", const)):
+    off6 = base + 1.0e6                                # large offset: few leading-word steps between min and max
+    off9 = base * 1.0e-3 + 1.0e9                       # offset >> spread (Float32: constant after rounding)
+    tiny = base * 1.0e-300 if dt == "float64" else base * 1.0e-30
+    zeros = torch.zeros_like(base); zeros[::2] = -0.0; zeros[:, :, :5] = base[:, :, :5]
+    naninf = base.clone(); naninf[3, 1, 0] = float("nan"); naninf[5, 2, 1] = float("inf"); naninf[7, 0, 2] = float("-inf")
+    neg = -torch.abs(base) - 2.0                       # all negative
+    cases = (("disc", disc), ("mild", mild), ("skew", skew), ("const", const), ("off6", off6), ("off9", off9),
+             ("tiny", tiny), ("zeros", zeros), ("naninf", naninf), ("neg", neg))
+    for nm, xs in cases:
         for kind in ("rank", "bulk"):
             cmp(f"{dt} {nm} ess_rhat {kind}", lambda: m.ess_rhat(xs, kind=kind))
         cmp(f"{dt} {nm} rhat tail", lambda: m.rhat(xs, kind="tail"))

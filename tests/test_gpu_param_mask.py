@@ -54,7 +54,7 @@ def test_masked_parameters_are_skipped_and_the_rest_is_unchanged(env):
 
 def test_all_missing_and_scalar(env):
     m, o = env
-    x, xm, miss = masked_case(o, P=3)
+    x = masked_case(o)[0][:, :, :3]
     xa = np.ma.masked_array(x.copy())
     xa[0, 0, :] = np.ma.masked
     S, R = m.ess_rhat(xa)
