@@ -169,18 +169,39 @@ CR_HD void cr_setup_body(const CrWork<T>& w, long long p) {
 }
 
 // ---- 2. count ---------------------------------------------------------------------------------------
+// The per-element bodies below take a BATCH of CR_U elements (i0, i0 + stride, ... below i1): every load / atomic
+// of the batch is issued before the first dependent store, so a thread keeps CR_U random accesses in flight (the
+// compiler may not hoist the loads of one element over the stores of the previous one: the pointers may alias).
+constexpr int CR_U = 4;
+
 template <typename T>
-CR_HD void cr_count_body(const CrWork<T>& w, const T* x, long long n, long long p, long long i) {
+CR_HD void cr_count_body(const CrWork<T>& w, const T* x, long long n, long long p, long long i0, long long stride,
+                         long long i1) {
   const CrMap<T> m = w.map[p];
   if (!(m.scale > (T)0)) return;   // flagged by the setup (NaN, Inf, constant): nothing to count
-  const T v = x[p * n + i];
-  unsigned fb = (unsigned)(long long)((v - m.vmin) * m.scale);
-  fb = fb < w.buckets ? fb : w.buckets - 1u;
-  const unsigned sh = (fb & 7u) * 4u;
-  const unsigned old = cr_atomic_add(&w.cw[p * w.nw + (fb >> 3)].x, 1u << sh);
-  const unsigned off = (old >> sh) & 15u;
-  if (off >= 15u) w.flag[p] = 1;   // the counter reaches 16 and spills into its neighbour
-  w.info[p * n + i] = fb | (off << 28);
+  T v[CR_U];
+#pragma unroll
+  for (int u = 0; u < CR_U; ++u) { const long long i = i0 + u * stride; v[u] = i < i1 ? x[p * n + i] : m.vmin; }
+  unsigned fb[CR_U], old[CR_U];
+#pragma unroll
+  for (int u = 0; u < CR_U; ++u) {
+    unsigned f = (unsigned)(long long)((v[u] - m.vmin) * m.scale);
+    fb[u] = f < w.buckets ? f : w.buckets - 1u;
+  }
+#pragma unroll
+  for (int u = 0; u < CR_U; ++u) {
+    old[u] = 0;
+    if (i0 + u * stride < i1) old[u] = cr_atomic_add(&w.cw[p * w.nw + (fb[u] >> 3)].x, 1u << ((fb[u] & 7u) * 4u));
+  }
+#pragma unroll
+  for (int u = 0; u < CR_U; ++u) {
+    const long long i = i0 + u * stride;
+    if (i < i1) {
+      const unsigned off = (old[u] >> ((fb[u] & 7u) * 4u)) & 15u;
+      if (off >= 15u) w.flag[p] = 1;   // the counter reaches 16 and spills into its neighbour
+      w.info[p * n + i] = fb[u] | (off << 28);
+    }
+  }
 }
 
 // ---- 3. scan ----------------------------------------------------------------------------------------
@@ -211,38 +232,60 @@ CR_HD void cr_scan3_body(const CrWork<T>& w, long long p, int s) {
 
 // ---- 4. place ---------------------------------------------------------------------------------------
 template <typename T>
-CR_HD void cr_place_body(const CrWork<T>& w, const T* x, long long n, long long p, long long i) {
-  const unsigned info = w.info[p * n + i];
-  const unsigned fb = info & 0x0fffffffu, off = info >> 28;
-  const unsigned sh = (fb & 7u) * 4u;
-  const uint2 e = w.cw[p * w.nw + (fb >> 3)];
-  const unsigned st = e.y + cr_nibsum(e.x & ((1u << sh) - 1u));
-  const unsigned c = (e.x >> sh) & 15u;
+CR_HD void cr_place_body(const CrWork<T>& w, const T* x, long long n, long long p, long long i0, long long stride,
+                         long long i1) {
+  unsigned info[CR_U];
+  uint2 e[CR_U];
+  T v[CR_U];
+#pragma unroll
+  for (int u = 0; u < CR_U; ++u) { const long long i = i0 + u * stride; info[u] = i < i1 ? w.info[p * n + i] : 0u; }
+#pragma unroll
+  for (int u = 0; u < CR_U; ++u) {
+    const long long i = i0 + u * stride;
+    e[u] = w.cw[p * w.nw + ((info[u] & 0x0fffffffu) >> 3)];
+    v[u] = i < i1 ? x[p * n + i] : (T)0;
+  }
   // the bucket's slots of S are needed when it is shared, or when it holds a central order statistic
   const unsigned mlo = (unsigned)((n - 1) >> 1), mhi = (unsigned)(n >> 1);
-  if ((c >= 2u || st == mlo || st == mhi) && (long long)st + off < n) w.srt[p * n + st + off] = x[p * n + i];
-  w.info[p * n + i] = st | (c << 24) | (off << 28);
+#pragma unroll
+  for (int u = 0; u < CR_U; ++u) {
+    const long long i = i0 + u * stride;
+    if (i < i1) {
+      const unsigned fb = info[u] & 0x0fffffffu, off = info[u] >> 28;
+      const unsigned sh = (fb & 7u) * 4u;
+      const unsigned st = e[u].y + cr_nibsum(e[u].x & ((1u << sh) - 1u));
+      const unsigned c = (e[u].x >> sh) & 15u;
+      if ((c >= 2u || st == mlo || st == mhi) && (long long)st + off < n) w.srt[p * n + st + off] = v[u];
+      w.info[p * n + i] = st | (c << 24) | (off << 28);
+    }
+  }
 }
 
 // ---- 5. rank ----------------------------------------------------------------------------------------
-// returns the doubled average rank r2 = lb + ub + 1 of element i
+// doubled average ranks r2 = lb + ub + 1 of a batch of elements (0 for the slots beyond i1)
 template <typename T>
-CR_HD long long cr_rank_body(const CrWork<T>& w, long long n, long long p, long long i) {
-  const unsigned info = w.info[p * n + i];
-  const unsigned st = info & 0x00ffffffu, c = (info >> 24) & 15u, off = info >> 28;
-  unsigned less = 0, eq = 1;
-  if (c >= 2u) {
-    const T* s = w.srt + p * n + st;
-    const T v = s[off];
-    eq = 0;
-    for (unsigned j = 0; j < c; ++j) {
-      const T y = s[j];
-      less += y < v;
-      eq += y == v;
+CR_HD void cr_rank_body(const CrWork<T>& w, long long n, long long p, long long i0, long long stride, long long i1,
+                        long long* r2) {
+  unsigned info[CR_U];
+#pragma unroll
+  for (int u = 0; u < CR_U; ++u) { const long long i = i0 + u * stride; info[u] = i < i1 ? w.info[p * n + i] : (1u << 24); }
+#pragma unroll
+  for (int u = 0; u < CR_U; ++u) {
+    const unsigned st = info[u] & 0x00ffffffu, c = (info[u] >> 24) & 15u, off = info[u] >> 28;
+    unsigned less = 0, eq = 1;
+    if (c >= 2u) {
+      const T* s = w.srt + p * n + st;
+      const T v = s[off];
+      eq = 0;
+      for (unsigned j = 0; j < c; ++j) {
+        const T y = s[j];
+        less += y < v;
+        eq += y == v;
+      }
     }
+    const long long lb = (long long)st + less;
+    r2[u] = (i0 + u * stride < i1) ? lb + (lb + eq) + 1 : 0;
   }
-  const long long lb = (long long)st + less;
-  return lb + (lb + eq) + 1;
 }
 
 // ---- 6. select --------------------------------------------------------------------------------------
@@ -313,7 +356,7 @@ __global__ void __launch_bounds__(CR_THREADS) crank_count_kernel(CrWork<T> w, co
   const long long p = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * CR_TILE;
   const long long t1 = t0 + CR_TILE < n ? t0 + CR_TILE : n;
-  for (long long i = t0 + threadIdx.x; i < t1; i += CR_THREADS) cr_count_body<T>(w, x, n, p, i);
+  for (long long i = t0 + threadIdx.x; i < t1; i += CR_U * CR_THREADS) cr_count_body<T>(w, x, n, p, i, CR_THREADS, t1);
 }
 // scan sweeps: one warp per (parameter, segment), global warp index = p * CR_NSEG + s; grid = pc * CR_NSEG / 8 CTAs
 template <typename T>
@@ -363,7 +406,7 @@ __global__ void __launch_bounds__(CR_THREADS) crank_place_kernel(CrWork<T> w, co
   const long long t0 = (long long)blockIdx.x * CR_TILE;
   const long long t1 = t0 + CR_TILE < n ? t0 + CR_TILE : n;
   if (w.flag[p]) return;   // (the counters of a flagged slab may be corrupt; the chunk is redone by the sort path)
-  for (long long i = t0 + threadIdx.x; i < t1; i += CR_THREADS) cr_place_body<T>(w, x, n, p, i);
+  for (long long i = t0 + threadIdx.x; i < t1; i += CR_U * CR_THREADS) cr_place_body<T>(w, x, n, p, i, CR_THREADS, t1);
 }
 template <typename T>
 __global__ void crank_median_kernel(CrWork<T> w, long long n, long long pc, double* __restrict__ thr) {

@@ -35,6 +35,7 @@ struct LargeEnv {
   long long crank_chunk = 0;  // cap on the parameters per chunk on the counting-rank path (0 = workspace-bound)
   long long* crank_chunks = nullptr;     // statistics: chunks ranked by counting / sent to the sort path
   long long* crank_fallbacks = nullptr;
+  int fft_tc = 0;                        // developer knob: columns per tile of the four-step FFT (0 = default 2)
   const void* ztab = nullptr;            // z for the doubled rank r2 at [r2 - 2] (ztab_kernel), or null: evaluate per element
 };
 
@@ -159,10 +160,21 @@ __global__ void __launch_bounds__(CR_THREADS) crank_rank_kernel(CrWork<T> w, lon
   if (w.flag[p]) return;
   const long long t0 = (long long)blockIdx.x * CR_TILE;
   const long long t1 = t0 + CR_TILE < n ? t0 + CR_TILE : n;
-  for (long long i = t0 + threadIdx.x; i < t1; i += CR_THREADS) {
-    const long long r2 = cr_rank_body<T>(w, n, p, i);
-    if (ranks_out) ranks_out[p * n + i] = 0.5 * (double)r2;
-    else Yout[p * n + i] = ztab ? __ldg(&ztab[r2 - 2]) : z_from_rank2<T>(r2, n);   // ztab[r2 - 2] = z_from_rank2(r2, n)
+  for (long long i0 = t0 + threadIdx.x; i0 < t1; i0 += CR_U * CR_THREADS) {
+    long long r2[CR_U];
+    cr_rank_body<T>(w, n, p, i0, CR_THREADS, t1, r2);
+    T z[CR_U];
+#pragma unroll
+    for (int u = 0; u < CR_U; ++u)   // ztab[r2 - 2] = z_from_rank2(r2, n) (ztab_kernel)
+      z[u] = (ranks_out || r2[u] == 0) ? (T)0 : (ztab ? __ldg(&ztab[r2[u] - 2]) : z_from_rank2<T>(r2[u], n));
+#pragma unroll
+    for (int u = 0; u < CR_U; ++u) {
+      const long long i = i0 + (long long)u * CR_THREADS;
+      if (i < t1) {
+        if (ranks_out) ranks_out[p * n + i] = 0.5 * (double)r2[u];
+        else Yout[p * n + i] = z[u];
+      }
+    }
   }
 }
 
@@ -343,6 +355,31 @@ __global__ void __launch_bounds__(LG_THREADS) chain_stats_kernel(const T* __rest
     const double qq = block_sum<LG_THREADS>(q, red);
     if (threadIdx.x == 0) { cm[wid] = m; cv[wid] = (T)(qq / (double)(g.niter - 1)); }
   }
+}
+
+// Short split chains (many-short-chains shapes: 50 draws per split chain): G lanes per chain, 32 / G chains per
+// warp (a warp per chain spends its time in ten 64-bit shuffles for a handful of values per lane).
+template <typename T, int G>
+__global__ void __launch_bounds__(LG_THREADS) chain_stats_group_kernel(const T* __restrict__ Y, SplitGeom g, long long params,
+                                                                       T* __restrict__ cm, T* __restrict__ cv) {
+  const long long nwork = params * g.nch;
+  const long long gid = (blockIdx.x * (long long)LG_THREADS + threadIdx.x) / G;
+  const int l = threadIdx.x % G;
+  const bool live = gid < nwork;
+  const long long wid = live ? gid : nwork - 1;   // (every lane takes part in the shuffles)
+  const long long param = wid / g.nch;
+  const int j = (int)(wid % g.nch);
+  const T* p = Y + param * (long long)g.n + g.chain_start(j);
+  double s = 0.0;
+  for (int t = l; t < g.niter; t += G) s += (double)p[t];
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const T m = (T)(s / (double)g.niter);
+  double q = 0.0;
+  for (int t = l; t < g.niter; t += G) { T d = p[t] - m; q = fma((double)d, (double)d, q); }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if (live && l == 0) { cm[wid] = m; cv[wid] = (T)(q / (double)(g.niter - 1)); }
 }
 
 // ---- FFT autocovariance, one CTA per (parameter, chain), shared-memory Stockham ------------------
@@ -750,7 +787,10 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
     if (best == 0) { msg = "FFTAutocovMethod: FFT length " + std::to_string(fftN) + " is beyond the four-step plan of this build"; return -4; }
     fN1 = best; fN2 = fftN / best;
     const long long capc = ((long long)env.smem_optin - 1024) / (long long)(4 * ts * fN1);  // column tiles: TC * 2 buffers of N1
-    for (int tc : {4, 3, 2, 1}) if (tc <= capc && fN2 % tc == 0) { fTC = tc; break; }
+    // columns per tile: 2 keeps every 32-byte sector of a strided column read fully used (Float64) and leaves room for
+    // three CTAs per SM; 4 (one CTA per SM) measured 12 % of the warps active (profiles/r2_fft_*: latency-bound)
+    const int tc_max = env.fft_tc > 0 ? env.fft_tc : 2;
+    for (int tc : {4, 3, 2, 1}) if (tc <= tc_max && tc <= capc && fN2 % tc == 0) { fTC = tc; break; }
     if (capc < 1) { msg = "FFTAutocovMethod: column FFT does not fit shared memory"; return -4; }
   }
   const long long nan_tiles = (n + NAN_TILE - 1) / NAN_TILE;
@@ -1015,6 +1055,8 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
         const long long nwork = pc * g.nch;
         if (g.niter >= 2048) {
           chain_stats_kernel<T, false><<<(unsigned)nwork, LG_THREADS, 0, st>>>(proxy, g, pc, cm, cv);
+        } else if (g.niter <= 128) {
+          chain_stats_group_kernel<T, 8><<<(unsigned)((nwork * 8 + LG_THREADS - 1) / LG_THREADS), LG_THREADS, 0, st>>>(proxy, g, pc, cm, cv);
         } else {
           chain_stats_kernel<T, true><<<(unsigned)((nwork * 32 + LG_THREADS - 1) / LG_THREADS), LG_THREADS, 0, st>>>(proxy, g, pc, cm, cv);
         }

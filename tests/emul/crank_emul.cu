@@ -40,7 +40,7 @@ static int emul(const T* x, long long n, long long pc, int bucket_factor, double
     for (long long t = tiles - 1; t >= 0; --t) {
       const long long t0 = t * CR_TILE, t1 = std::min<long long>(t0 + CR_TILE, n);
       for (int th = CR_THREADS - 1; th >= 0; --th)
-        for (long long i = t0 + th; i < t1; i += CR_THREADS) cr_count_body<T>(w, x, n, p, i);
+        for (long long i = t0 + th; i < t1; i += CR_U * CR_THREADS) cr_count_body<T>(w, x, n, p, i, CR_THREADS, t1);
     }
   // 3. scan
   for (long long p = 0; p < pc; ++p) for (int s = 0; s < CR_NSEG; ++s) cr_scan1_body<T>(w, p, s);
@@ -48,13 +48,26 @@ static int emul(const T* x, long long n, long long pc, int bucket_factor, double
   // 4. place
   for (long long p = 0; p < pc; ++p) {
     if (w.flag[p]) continue;
-    for (long long i = 0; i < n; ++i) cr_place_body<T>(w, x, n, p, i);
+    for (long long t = 0; t < tiles; ++t) {
+      const long long t0 = t * CR_TILE, t1 = std::min<long long>(t0 + CR_TILE, n);
+      for (int th = 0; th < CR_THREADS; ++th)
+        for (long long i = t0 + th; i < t1; i += CR_U * CR_THREADS) cr_place_body<T>(w, x, n, p, i, CR_THREADS, t1);
+    }
   }
   // 5. rank, 6. median
   for (long long p = 0; p < pc; ++p) {
     flags[p] = w.flag[p];
     if (w.flag[p]) { med[p] = 0.0; continue; }
-    for (long long i = 0; i < n; ++i) ranks[p * n + i] = 0.5 * (double)cr_rank_body<T>(w, n, p, i);
+    for (long long t = 0; t < tiles; ++t) {
+      const long long t0 = t * CR_TILE, t1 = std::min<long long>(t0 + CR_TILE, n);
+      for (int th = 0; th < CR_THREADS; ++th)
+        for (long long i = t0 + th; i < t1; i += CR_U * CR_THREADS) {
+          long long r2[CR_U];
+          cr_rank_body<T>(w, n, p, i, CR_THREADS, t1, r2);
+          for (int u = 0; u < CR_U; ++u)
+            if (i + (long long)u * CR_THREADS < t1) ranks[p * n + i + (long long)u * CR_THREADS] = 0.5 * (double)r2[u];
+        }
+    }
     med[p] = (double)cr_median_body<T>(w, n, p);
   }
   return 0;
