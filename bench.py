@@ -114,15 +114,15 @@ CONFIGS = {c.name: c for c in (
     Config("c3fft", 1_000_000, 4, 1000, "float64", 1, 1,
            "params/sec for ess(kind=:bulk, FFTAutocovMethod), 1e6x4x1000 f64",
            "ess(kind=:bulk, FFTAutocovMethod, split_chains=2, maxlag=250) on 1e6 draws x 4 chains x 1000 params Float64, AR(1) phi=0.5",
-           "large-slab pipeline (segmented sort + four-step FFT, N = 2^20)"),
+           "large-slab pipeline (counting rank mcd_crank + four-step FFT, N = 2^19 >= niter + maxlag)"),
     Config("c4nested", 100, 2048, 10_000, "float64", 1, 1,
            "params/sec for rhat_nested(kind=:rank), 2048 chains in 32 superchains x 100 draws x 1e4 params f64",
            "rhat_nested(kind=:rank, split_chains=2), superchain_ids = repeat(1:32, inner=64), on 100 draws x 2048 chains x 1e4 params Float64, AR(1) phi=0.5",
-           "large-slab pipeline (segmented sort + nested moments)"),
+           "large-slab pipeline (counting rank mcd_crank + split-chain moments + nested R-hat)"),
     Config("c5bda", 4000, 8, 100_000, "float32", 2, 2,
            "params/sec for ess(kind=median) + ess(kind=std) with BDAAutocovMethod, 4000x8x1e5 f32",
            "ess(kind=median) and ess(kind=std), BDAAutocovMethod, split_chains=2, maxlag=250, on 4000 draws x 8 chains x 1e5 params Float32, AR(1) phi=0.5 (two reference calls per step)",
-           "large-slab pipeline / slab kernel"),
+           "mcd::big_kernel<float> (slab resident in one SM's shared memory via TMA)"),
 )}
 
 
@@ -370,14 +370,24 @@ def gpu_arm(args, cfg):
 
     peak, peak_src = measured_peak_gbs()
     achieved = shard * cfg.bytes_per_param / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM traffic of the dominant kernel from its last `ncu --set full` capture (profiles/roofline_traffic.json, written
+    # by scripts/ncu_traffic.py): used only while the kernel source it was taken on is unchanged (sha-256 stamp)
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
+            import hashlib
             tj = json.load(open(tp)).get(cfg.name)
-            traffic = tj["dram_bytes_per_param"] * shard if tj else None
+            if tj:
+                with open(os.path.join(ROOT, tj["kernel_source"]), "rb") as f:
+                    sha = hashlib.sha256(f.read()).hexdigest()[:16]
+                if sha == tj["source_sha16"]:
+                    traffic = tj["dram_bytes_per_param"] * shard
+                    traffic_src = f"ncu --set full capture of this kernel source ({tj['kernel_source']} sha {sha}): {tj['capture']}"
+                else:
+                    traffic_src = "stale: the kernel source changed since the last ncu capture"
         except Exception:
-            traffic = None
+            traffic, traffic_src = None, None
     line = {
         "metric": cfg.metric, "value": value, "unit": "params/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -388,8 +398,7 @@ def gpu_arm(args, cfg):
                    "l2": "input per GPU (%.1f GB) is larger than the 126 MB L2; no flush needed"
                          % (shard * cfg.draws * cfg.chains * cfg.elem / 1e9)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_source": "profiles/roofline_traffic.json (ncu --set full capture of this kernel; "
-                                                           "stamped with the kernel source hash it was taken on)" if traffic else None,
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "kernel": cfg.kernel, "path_code": last_path,
                      "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": shard * cfg.bytes_per_param,
                      "algorithmic_bytes_per_param": cfg.bytes_per_param},

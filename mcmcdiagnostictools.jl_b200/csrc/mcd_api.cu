@@ -63,6 +63,7 @@ struct mcd_ctx {
   int crank_factor = 4;    // counting rank: fine buckets per value
   long long crank_chunk = 0;   // counting rank: cap on the parameters per chunk (0 = workspace-bound)
   int fft_tc = 0;          // developer knob: columns per tile of the four-step FFT (0 = default)
+  int fft_full = 0;        // developer knob: 1 = FFT length nextprod(2 niter - 1) on the large path (default: niter + maxlag)
   // stats
   long long crank_chunks = 0, crank_fallbacks = 0;
   long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -731,7 +732,7 @@ static int run_device(mcd_ctx* ctx, const T* dx, long long params, const SplitGe
   env.d_chain_inds = ctx->d_chain_inds;
   env.rel_ess_max = (double)rel_ess_max_of<T>((long long)g.niter * g.nch);
   env.use_crank = ctx->use_crank; env.crank_factor = ctx->crank_factor; env.crank_chunk = ctx->crank_chunk;
-  env.fft_tc = ctx->fft_tc;
+  env.fft_tc = ctx->fft_tc; env.fft_full = ctx->fft_full;
   env.crank_chunks = &ctx->crank_chunks; env.crank_fallbacks = &ctx->crank_fallbacks;
   // the counting rank turns ranks into z by a table lookup while the table stays cache-sized (<= 32 MB)
   if (ctx->use_crank && g.n >= 1024 && (size_t)g.n * 4 * sizeof(T) <= ((size_t)32 << 20)) {
@@ -1248,6 +1249,7 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   else if (k == "use_big") { ctx->use_big = (int)value; }
   else if (k == "use_crank") { ctx->use_crank = (int)value; }
   else if (k == "crank_factor") { if (value < 1 || value > 64) return fail(ctx, MCD_EINVAL, "crank_factor in 1..64"); ctx->crank_factor = (int)value; }
+  else if (k == "fft_full") { ctx->fft_full = value ? 1 : 0; }
   else if (k == "fft_tc") { if (value < 0 || value > 4) return fail(ctx, MCD_EINVAL, "fft_tc in 0..4"); ctx->fft_tc = (int)value; }
   else if (k == "crank_chunk") { if (value < 0) return fail(ctx, MCD_EINVAL, "crank_chunk >= 0"); ctx->crank_chunk = value; }
   else if (k == "slab_wide") ctx->slab_wide = value ? 1 : 0;

@@ -36,6 +36,7 @@ struct LargeEnv {
   long long* crank_chunks = nullptr;     // statistics: chunks ranked by counting / sent to the sort path
   long long* crank_fallbacks = nullptr;
   int fft_tc = 0;                        // developer knob: columns per tile of the four-step FFT (0 = default 2)
+  int fft_full = 0;                      // developer knob: 1 = transform length nextprod(2 niter - 1) as the reference pads
   const void* ztab = nullptr;            // z for the doubled rank r2 at [r2 - 2] (ztab_kernel), or null: evaluate per element
 };
 
@@ -767,7 +768,12 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   }
   needs_sort |= combine == CB_MCSE_QUANTILE;
   const bool use_fft = any_ess && method == 1 && !ess_nan;
-  const long long fftN = use_fft ? nextprod23_l(2ll * g.niter - 1) : 0;
+  // Transform length.  The reference pads to nextprod([2, 3], 2 niter - 1) (src/ess_rhat.jl:103-118), which makes the
+  // circular correlation linear for EVERY lag; only lags <= maxlag are ever read (:181-195), and those are free of
+  // wrap-around as soon as N >= niter + maxlag (a term x_t x_{t+k-N} needs t >= N - k >= niter).  For long chains
+  // (C3: niter = 5e5, maxlag = 250) this halves N: 2^19 instead of 2^20.  Same quantity, different rounding (1e-15).
+  const long long fft_need = env.fft_full ? 2ll * g.niter - 1 : std::min<long long>(2ll * g.niter - 1, (long long)g.niter + maxlag);
+  const long long fftN = use_fft ? nextprod23_l(fft_need) : 0;
   // FFT plan: one CTA per chain while two N-point complex buffers fit shared memory, else four-step
   const bool fft_big = use_fft && (size_t)fftN * 4 * ts > (size_t)env.smem_optin - 1024;
   long long fN1 = 0, fN2 = 0;

@@ -12,16 +12,17 @@ x = m.generate_ar1(0.5, np.sqrt(0.75), 1_000_000, 4, P, seed=1)
 torch.cuda.synchronize()
 fn = lambda: m.ess(x, kind="bulk", autocov_method=m.FFTAutocovMethod())
 ref = None
-for crank in (0, 1):
-    for tc in (4, 2, 1):
-        ctx.set_option("use_crank", crank); ctx.set_option("fft_tc", tc)
-        r = fn(); torch.cuda.synchronize()
-        ts = []
-        for _ in range(2):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); r = fn(); b.record(); torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
-        if ref is None:
-            ref = r.clone()
-        print(f"C3 P={P} use_crank={crank} fft_tc={tc}: {min(ts):8.3f} ms  {P / min(ts) * 1e3:8.1f} params/s  frac {P / min(ts) * 1e3 / 204631:.4f}  identical={bool((r == ref).all())}", flush=True)
-ctx.set_option("fft_tc", 0); ctx.set_option("use_crank", 1)
+for full, tc, crank in ((1, 4, 0), (1, 2, 1), (0, 2, 1), (0, 4, 1), (0, 1, 1)):
+    ctx.set_option("use_crank", crank); ctx.set_option("fft_tc", tc); ctx.set_option("fft_full", full)
+    r = fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); r = fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    if ref is None:
+        ref = r.clone()
+    rel = float(((r - ref).abs() / ref.abs()).max())
+    print(f"C3 P={P} fft_full={full} fft_tc={tc} use_crank={crank}: {min(ts):8.3f} ms  {P / min(ts) * 1e3:8.1f} params/s  "
+          f"frac {P / min(ts) * 1e3 / 204631:.4f}  max rel diff vs first = {rel:.2e}", flush=True)
+ctx.set_option("fft_tc", 0); ctx.set_option("use_crank", 1); ctx.set_option("fft_full", 0)
