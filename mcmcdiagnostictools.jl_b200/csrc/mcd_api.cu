@@ -63,7 +63,8 @@ struct mcd_ctx {
   int crank_factor = 4;    // counting rank: fine buckets per value
   long long crank_chunk = 0;   // counting rank: cap on the parameters per chunk (0 = workspace-bound)
   int fft_tc = 0;          // developer knob: columns per tile of the four-step FFT (0 = default)
-  int fft_full = 0;        // developer knob: 1 = FFT length nextprod(2 niter - 1) on the large path (default: niter + maxlag)
+  int fft_full = 0;        // developer knob: 1 = FFT length nextprod(2 niter - 1) (default: niter + maxlag)
+  int fft_pair = 1;        // developer knob: 0 = four-step FFT with one transform per chain (round-1 data flow)
   // stats
   long long crank_chunks = 0, crank_fallbacks = 0;
   long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -394,7 +395,9 @@ static int run_slab(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   a.ess_out = d_ess; a.rhat_out = d_rhat; a.arr_out = d_arr;
   a.nbuckets = std::min(std::max(next_pow2(g.n), SLAB_THREADS), 16384);
   a.bucket_limit = ctx->bucket_limit;
-  a.fft_n = (pg.method == MCD_AUTOCOV_FFT && pg.want_ess && !pg.ess_nan) ? (int)nextprod23(2ll * g.niter - 1) : 0;
+  // transform length: lags <= maxlag are free of wrap-around once N >= niter + maxlag (see run_large in mcd_large.cuh)
+  const long long fft_need = ctx->fft_full ? 2ll * g.niter - 1 : std::min<long long>(2ll * g.niter - 1, (long long)g.niter + pg.maxlag);
+  a.fft_n = (pg.method == MCD_AUTOCOV_FFT && pg.want_ess && !pg.ess_nan) ? (int)nextprod23(fft_need) : 0;
   a.cps = (int)pg.cps; a.nsuper = (int)pg.nsuper;
   a.mcse_p = pg.mcse_p;
   a.flags = ctx->d_flags;
@@ -732,7 +735,7 @@ static int run_device(mcd_ctx* ctx, const T* dx, long long params, const SplitGe
   env.d_chain_inds = ctx->d_chain_inds;
   env.rel_ess_max = (double)rel_ess_max_of<T>((long long)g.niter * g.nch);
   env.use_crank = ctx->use_crank; env.crank_factor = ctx->crank_factor; env.crank_chunk = ctx->crank_chunk;
-  env.fft_tc = ctx->fft_tc; env.fft_full = ctx->fft_full;
+  env.fft_tc = ctx->fft_tc; env.fft_full = ctx->fft_full; env.fft_pair = ctx->fft_pair;
   env.crank_chunks = &ctx->crank_chunks; env.crank_fallbacks = &ctx->crank_fallbacks;
   // the counting rank turns ranks into z by a table lookup while the table stays cache-sized (<= 32 MB)
   if (ctx->use_crank && g.n >= 1024 && (size_t)g.n * 4 * sizeof(T) <= ((size_t)32 << 20)) {
@@ -1249,6 +1252,7 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   else if (k == "use_big") { ctx->use_big = (int)value; }
   else if (k == "use_crank") { ctx->use_crank = (int)value; }
   else if (k == "crank_factor") { if (value < 1 || value > 64) return fail(ctx, MCD_EINVAL, "crank_factor in 1..64"); ctx->crank_factor = (int)value; }
+  else if (k == "fft_pair") { ctx->fft_pair = value ? 1 : 0; }
   else if (k == "fft_full") { ctx->fft_full = value ? 1 : 0; }
   else if (k == "fft_tc") { if (value < 0 || value > 4) return fail(ctx, MCD_EINVAL, "fft_tc in 0..4"); ctx->fft_tc = (int)value; }
   else if (k == "crank_chunk") { if (value < 0) return fail(ctx, MCD_EINVAL, "crank_chunk >= 0"); ctx->crank_chunk = value; }

@@ -37,6 +37,7 @@ struct LargeEnv {
   long long* crank_fallbacks = nullptr;
   int fft_tc = 0;                        // developer knob: columns per tile of the four-step FFT (0 = default 2)
   int fft_full = 0;                      // developer knob: 1 = transform length nextprod(2 niter - 1) as the reference pads
+  int fft_pair = 1;                      // four-step FFT: two real chains per transform + one inverse per parameter
   const void* ztab = nullptr;            // z for the doubled rank r2 at [r2 - 2] (ztab_kernel), or null: evaluate per element
 };
 
@@ -488,15 +489,116 @@ __global__ void __launch_bounds__(LG_THREADS) fft4_rows_kernel(Cx<T>* __restrict
   }
 }
 
+// ---- paired variant (round 2): two real chains per complex transform, ONE inverse per parameter ----------------
+// The chains are real, so chains 2q and 2q+1 ride one complex transform z = a + i b, and
+//   |A(k)|^2 + |B(k)|^2 = (|Z(k)|^2 + |Z(N-k)|^2) / 2.
+// Only the chain-AVERAGE of the autocovariances is ever used (mean_autocov, ess_rhat.jl:181-195), and the transform
+// is linear: the power spectra of all chains of a parameter are summed and inverted once.  The reference weights
+// chain j by var_j / c_j[0] with c_j[0] = (niter - 1) var_j (its own lag-0 term), i.e. every chain by 1 / (niter - 1):
+// mean_j(c_j[k] / c_j[0] var_j) = (sum_j c_j[k] / sum_j c_j[0]) mean_j(var_j), which ess_kernel forms from the summed
+// series (scale-free; the two differ by the rounding of c_j[0] only).  Per parameter: nch / 2 forward + 1 inverse
+// transforms instead of nch + nch.  With k = k1 + N1 k2 the mirror N - k of row k1 > 0 is row N1 - k1 read backwards
+// (k2 -> N2 - 1 - k2); row 0 mirrors onto itself (k2 -> (N2 - k2) mod N2): a CTA takes a row and its mirror row.
+template <typename T>
+__global__ void __launch_bounds__(LG_THREADS) fft4p_cols_fwd_kernel(const T* __restrict__ Y, SplitGeom g, const T* __restrict__ cm,
+                                                                    int npair, int N1, int N2, int TC,
+                                                                    const Cx<T>* __restrict__ tw1, const Cx<T>* __restrict__ twh,
+                                                                    const Cx<T>* __restrict__ twl, Cx<T>* __restrict__ B) {
+  extern __shared__ __align__(16) unsigned char smem_fft[];
+  Cx<T>* buf = reinterpret_cast<Cx<T>*>(smem_fft);          // [TC][2][N1]
+  const int tiles = N2 / TC;
+  const long long pid = blockIdx.x / tiles;                  // (parameter, pair) within the chunk
+  const int col0 = (int)(blockIdx.x % tiles) * TC;
+  const long long param = pid / npair;
+  const int ja = 2 * (int)(pid % npair), jb = ja + 1;
+  const T* pa = Y + param * (long long)g.n + g.chain_start(ja);
+  const T ma = cm[param * g.nch + ja];
+  const bool hasb = jb < g.nch;
+  const T* pb = hasb ? Y + param * (long long)g.n + g.chain_start(jb) : pa;
+  const T mb = hasb ? cm[param * g.nch + jb] : (T)0;
+  for (int idx = threadIdx.x; idx < N1 * TC; idx += LG_THREADS) {
+    const int n1 = idx / TC, c = idx - n1 * TC;
+    const long long nn = (long long)N2 * n1 + col0 + c;
+    Cx<T> v;
+    v.x = nn < g.niter ? (T)(pa[nn] - ma) : (T)0;
+    v.y = (hasb && nn < g.niter) ? (T)(pb[nn] - mb) : (T)0;
+    buf[(2 * c) * N1 + n1] = v;
+  }
+  __syncthreads();
+  const long long N = (long long)N1 * N2;
+  Cx<T>* Bc = B + pid * N;
+  for (int c = 0; c < TC; ++c) {
+    Cx<T>* r = fft_block<T, LG_THREADS>(buf + (2 * c) * N1, buf + (2 * c + 1) * N1, N1, tw1, false);
+    for (int k1 = threadIdx.x; k1 < N1; k1 += LG_THREADS) {
+      const Cx<T> w = big_twiddle<T>(twh, twl, (long long)(col0 + c) * k1, false);
+      const Cx<T> u = r[k1];
+      Cx<T> o; o.x = u.x * w.x - u.y * w.y; o.y = u.x * w.y + u.y * w.x;
+      Bc[(long long)k1 * N2 + col0 + c] = o;
+    }
+  }
+}
+
+// grid = parameters x (N1 / 2 + 1) row pairs.  Shared memory: three N2-point complex buffers + the N2 summed powers.
+// The inverse rows are written over pair 0's buffer of the parameter (this CTA is the only reader of those rows).
+template <typename T>
+__global__ void __launch_bounds__(LG_THREADS) fft4p_rows_kernel(Cx<T>* __restrict__ B, int npair, int N1, int N2,
+                                                                const Cx<T>* __restrict__ tw2, const Cx<T>* __restrict__ twh,
+                                                                const Cx<T>* __restrict__ twl) {
+  extern __shared__ __align__(16) unsigned char smem_fft[];
+  Cx<T>* X0 = reinterpret_cast<Cx<T>*>(smem_fft);
+  Cx<T>* X1 = X0 + N2;
+  Cx<T>* X2 = X1 + N2;
+  T* P = reinterpret_cast<T*>(X2 + N2);
+  const int nrp = N1 / 2 + 1;
+  const long long param = blockIdx.x / nrp;
+  const int k1 = (int)(blockIdx.x % nrp);
+  const int k1m = (N1 - k1) % N1;                 // the mirror row
+  const bool self = k1m == k1;                    // row 0, and row N1 / 2 of an even N1
+  const long long N = (long long)N1 * N2;
+  for (int t = threadIdx.x; t < N2; t += LG_THREADS) P[t] = (T)0;
+  for (int q = 0; q < npair; ++q) {
+    const Cx<T>* Bq = B + (param * npair + q) * N;
+    for (int t = threadIdx.x; t < N2; t += LG_THREADS) {
+      X0[t] = Bq[(long long)k1 * N2 + t];
+      if (!self) X1[t] = Bq[(long long)k1m * N2 + t];
+    }
+    __syncthreads();
+    Cx<T>* f0 = fft_block<T, LG_THREADS>(X0, X2, N2, tw2, false);
+    Cx<T>* fm = f0;
+    if (!self) fm = fft_block<T, LG_THREADS>(X1, f0 == X0 ? X2 : X0, N2, tw2, false);
+    for (int t = threadIdx.x; t < N2; t += LG_THREADS) {
+      const int m = (k1 == 0) ? (N2 - t) % N2 : N2 - 1 - t;     // k2 of the mirror frequency in row k1m
+      const Cx<T> a = f0[t], b = fm[m];
+      P[t] += (T)0.5 * ((a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y));
+    }
+    __syncthreads();
+  }
+  Cx<T>* D = B + param * npair * N;
+  for (int pass = 0; pass < (self ? 1 : 2); ++pass) {
+    const int kr = pass == 0 ? k1 : k1m;
+    // the power of row k1m at k2 is the power of row k1 at its mirror k2 (k1m > 0 here: N2 - 1 - k2)
+    for (int t = threadIdx.x; t < N2; t += LG_THREADS) { Cx<T> c; c.x = pass == 0 ? P[t] : P[N2 - 1 - t]; c.y = (T)0; X0[t] = c; }
+    __syncthreads();
+    Cx<T>* r = fft_block<T, LG_THREADS>(X0, X1, N2, tw2, true);
+    for (int n2 = threadIdx.x; n2 < N2; n2 += LG_THREADS) {
+      const Cx<T> w = big_twiddle<T>(twh, twl, (long long)n2 * kr, true);
+      const Cx<T> u = r[n2];
+      Cx<T> v; v.x = u.x * w.x - u.y * w.y; v.y = u.x * w.y + u.y * w.x;
+      D[(long long)kr * N2 + n2] = v;
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(LG_THREADS) fft4_cols_inv_kernel(const Cx<T>* __restrict__ D, int N1, int N2, int TC,
                                                                    const Cx<T>* __restrict__ tw1, int maxlag, int tiles,
-                                                                   T* __restrict__ ac) {
+                                                                   T* __restrict__ ac, long long dstride) {
   extern __shared__ __align__(16) unsigned char smem_fft[];
   Cx<T>* buf = reinterpret_cast<Cx<T>*>(smem_fft);          // [TC][2][N1]
   const long long wid = blockIdx.x / tiles;
   const int col0 = (int)(blockIdx.x % tiles) * TC;
-  const Cx<T>* Dc = D + wid * (long long)N1 * N2;
+  const Cx<T>* Dc = D + wid * dstride;   // dstride = N1 N2 (a buffer per chain) or npair N1 N2 (one per parameter)
   for (int idx = threadIdx.x; idx < N1 * TC; idx += LG_THREADS) {
     const int k1 = idx / TC, c = idx - k1 * TC;
     buf[(2 * c) * N1 + k1] = Dc[(long long)k1 * N2 + col0 + c];
@@ -532,7 +634,8 @@ struct EssArgs {
   int want_ess, method, maxlag, relative, ess_nan;
   T rel_ess_max;
   T* gam;          // [params][maxlag + 1 + LAG_BATCH] scratch
-  const T* ac;     // FFT: [params][nch][maxlag+1]
+  const T* ac;     // FFT: [params][nch][maxlag+1] raw Re c[k] per chain, or (ac_summed) [params][maxlag+1] summed over the chains
+  int ac_summed = 0;
   double* r_ess; double* r_rhat;
 };
 
@@ -562,7 +665,15 @@ __global__ void __launch_bounds__(LG_THREADS) ess_kernel(const EssArgs<T> a) {
   T* gamma = a.gam + param * (long long)(maxlag + 1 + LAG_BATCH);
   const T* Yp = a.Y + param * (long long)g.n;
   int have = 0;
-  if (a.method == 1) {
+  if (a.method == 1 && a.ac_summed) {
+    // one series per parameter: sum over the chains of the raw Re c[k] (paired four-step FFT).  mean_i(c[k,i] /
+    // c[0,i] var_i) with c[0,i] = (niter - 1) var_i is (sum_i c[k,i] / sum_i c[0,i]) mean_i(var_i)
+    const T* ac = a.ac + param * (long long)(maxlag + 1);
+    const T unc = (T)(niter - 1) / (T)niter;
+    for (int k = threadIdx.x; k <= maxlag; k += LG_THREADS) gamma[k] = (ac[k] / ac[0]) * W * unc;
+    __syncthreads();
+    have = maxlag;
+  } else if (a.method == 1) {
     const T* ac = a.ac + param * (long long)g.nch * (maxlag + 1);
     const T unc = (T)(niter - 1) / (T)niter;
     for (int k = threadIdx.x; k <= maxlag; k += LG_THREADS) {
@@ -799,6 +910,10 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
     for (int tc : {4, 3, 2, 1}) if (tc <= tc_max && tc <= capc && fN2 % tc == 0) { fTC = tc; break; }
     if (capc < 1) { msg = "FFTAutocovMethod: column FFT does not fit shared memory"; return -4; }
   }
+  // paired variant: three N2-point complex buffers + N2 powers per CTA of the row kernel
+  const bool fft_pair = fft_big && env.fft_pair && (size_t)fN2 * 7 * ts + 1024 <= (size_t)env.smem_optin;
+  const int npair = (g.nch + 1) / 2;
+  const long long fft_bufs = fft_pair ? npair : g.nch;   // N-point complex buffers per parameter
   const long long nan_tiles = (n + NAN_TILE - 1) / NAN_TILE;
   const long long gam_stride = maxlag + 1 + LAG_BATCH;
   // counting rank: every use of the sorted copy must be one it provides (ranks, median)
@@ -820,7 +935,7 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   per += 2 * al((size_t)g.nch * ts);
   if (any_ess) per += al((size_t)gam_stride * ts);
   if (use_fft) per += al((size_t)g.nch * (maxlag + 1) * ts);
-  if (fft_big) per += al((size_t)g.nch * fftN * 2 * ts);
+  if (fft_big) per += al((size_t)fft_bufs * fftN * 2 * ts);
   if (any_nested) per += al((size_t)2 * nsuper * 8);
   per += 256 * 2;  // thresholds, nnan, results (per-param scalars; generous)
   if (crankable) per += al((size_t)cr_nw * 8) + al((size_t)CR_NSEG * 4) + 64;
@@ -849,7 +964,7 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   const size_t oAC = carve(use_fft ? (size_t)chunk * g.nch * (maxlag + 1) * ts : 0);
   const size_t oNS = carve(any_nested ? (size_t)chunk * 2 * nsuper * 8 : 0);
   const size_t oTW = carve(use_fft ? (size_t)(fft_big ? (fN1 + fN2 + (fftN >> 10) + 1 + 1024) : fftN) * 2 * ts : 0);
-  const size_t oFB = carve(fft_big ? (size_t)chunk * g.nch * fftN * 2 * ts : 0);
+  const size_t oFB = carve(fft_big ? (size_t)chunk * fft_bufs * fftN * 2 * ts : 0);
   const size_t oTHR = carve(scal), oTHR2 = carve(scal), oEX0 = carve(scal), oEX1 = carve(scal);
   const size_t oNNX = carve(scal), oNNY = carve(scal);
   const size_t oCRW = carve(crankable ? (size_t)chunk * cr_nw * 8 : 0);
@@ -898,6 +1013,10 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
     LCU(cudaFuncSetAttribute(fft4_cols_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fTC * fN1 * 4 * ts)));
     LCU(cudaFuncSetAttribute(fft4_cols_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fTC * fN1 * 4 * ts)));
     LCU(cudaFuncSetAttribute(fft4_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fN2 * 4 * ts)));
+    if (fft_pair) {
+      LCU(cudaFuncSetAttribute(fft4p_cols_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fTC * fN1 * 4 * ts)));
+      LCU(cudaFuncSetAttribute(fft4p_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fN2 * 7 * ts)));
+    }
   }
   const T rel_ess_max = (T)env.rel_ess_max;
   const int ew_blocks_cap = env.sm_count * 16;
@@ -1078,21 +1197,34 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
           }
           if (want_ess && fft_big) {
             const int tiles_f = (int)(fN2 / fTC);
-            fft4_cols_fwd_kernel<T><<<(unsigned)(nwork * tiles_f), LG_THREADS, (size_t)fTC * fN1 * 4 * ts, st>>>(
-                proxy, g, cm, (int)fN1, (int)fN2, fTC, tw1, twh, twl, fB);
-            LAUNCHED();
-            fft4_rows_kernel<T><<<(unsigned)(nwork * fN1), LG_THREADS, (size_t)fN2 * 4 * ts, st>>>(fB, (int)fN1, (int)fN2, tw2, twh, twl);
-            LAUNCHED();
             const long long ncols = std::min<long long>(fN2, (long long)maxlag + 1);
             const int tiles_i = (int)((ncols + fTC - 1) / fTC);
-            fft4_cols_inv_kernel<T><<<(unsigned)(nwork * tiles_i), LG_THREADS, (size_t)fTC * fN1 * 4 * ts, st>>>(
-                fB, (int)fN1, (int)fN2, fTC, tw1, maxlag, tiles_i, ac);
-            LAUNCHED();
+            if (fft_pair) {
+              fft4p_cols_fwd_kernel<T><<<(unsigned)(pc * npair * tiles_f), LG_THREADS, (size_t)fTC * fN1 * 4 * ts, st>>>(
+                  proxy, g, cm, npair, (int)fN1, (int)fN2, fTC, tw1, twh, twl, fB);
+              LAUNCHED();
+              fft4p_rows_kernel<T><<<(unsigned)(pc * (fN1 / 2 + 1)), LG_THREADS, (size_t)fN2 * 7 * ts, st>>>(
+                  fB, npair, (int)fN1, (int)fN2, tw2, twh, twl);
+              LAUNCHED();
+              fft4_cols_inv_kernel<T><<<(unsigned)(pc * tiles_i), LG_THREADS, (size_t)fTC * fN1 * 4 * ts, st>>>(
+                  fB, (int)fN1, (int)fN2, fTC, tw1, maxlag, tiles_i, ac, (long long)npair * fftN);
+              LAUNCHED();
+            } else {
+              fft4_cols_fwd_kernel<T><<<(unsigned)(nwork * tiles_f), LG_THREADS, (size_t)fTC * fN1 * 4 * ts, st>>>(
+                  proxy, g, cm, (int)fN1, (int)fN2, fTC, tw1, twh, twl, fB);
+              LAUNCHED();
+              fft4_rows_kernel<T><<<(unsigned)(nwork * fN1), LG_THREADS, (size_t)fN2 * 4 * ts, st>>>(fB, (int)fN1, (int)fN2, tw2, twh, twl);
+              LAUNCHED();
+              fft4_cols_inv_kernel<T><<<(unsigned)(nwork * tiles_i), LG_THREADS, (size_t)fTC * fN1 * 4 * ts, st>>>(
+                  fB, (int)fN1, (int)fN2, fTC, tw1, maxlag, tiles_i, ac, fftN);
+              LAUNCHED();
+            }
           }
           EssArgs<T> ea;
           ea.Y = proxy; ea.g = g; ea.params = pc; ea.cm = cm; ea.cv = cv;
           ea.want_ess = want_ess; ea.method = method; ea.maxlag = maxlag; ea.relative = relative; ea.ess_nan = ess_nan;
           ea.rel_ess_max = rel_ess_max; ea.gam = gam; ea.ac = ac; ea.r_ess = r_ess; ea.r_rhat = r_rhat;
+          ea.ac_summed = want_ess && fft_big && fft_pair;
           ess_kernel<T><<<(unsigned)pc, LG_THREADS, 0, st>>>(ea);
           LAUNCHED();
         }

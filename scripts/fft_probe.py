@@ -1,5 +1,6 @@
-"""Developer probe: columns per tile of the four-step FFT (C3 shape: 1e6 draws x 4 chains, N = 2^20 per split chain).
-python scripts/fft_probe.py [P]"""
+"""Developer probe: the four-step FFT on the C3 shape (1e6 draws x 4 chains): transform length, columns per tile,
+paired / summed data flow; then agreement of the paired path with the per-chain path and with the direct method on
+other shapes.   python scripts/fft_probe.py [P]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -12,8 +13,8 @@ x = m.generate_ar1(0.5, np.sqrt(0.75), 1_000_000, 4, P, seed=1)
 torch.cuda.synchronize()
 fn = lambda: m.ess(x, kind="bulk", autocov_method=m.FFTAutocovMethod())
 ref = None
-for full, tc, crank in ((1, 4, 0), (1, 2, 1), (0, 2, 1), (0, 4, 1), (0, 1, 1)):
-    ctx.set_option("use_crank", crank); ctx.set_option("fft_tc", tc); ctx.set_option("fft_full", full)
+for full, tc, pair in ((1, 4, 0), (0, 2, 0), (0, 2, 1)):
+    ctx.set_option("fft_tc", tc); ctx.set_option("fft_full", full); ctx.set_option("fft_pair", pair)
     r = fn(); torch.cuda.synchronize()
     ts = []
     for _ in range(2):
@@ -23,6 +24,17 @@ for full, tc, crank in ((1, 4, 0), (1, 2, 1), (0, 2, 1), (0, 4, 1), (0, 1, 1)):
     if ref is None:
         ref = r.clone()
     rel = float(((r - ref).abs() / ref.abs()).max())
-    print(f"C3 P={P} fft_full={full} fft_tc={tc} use_crank={crank}: {min(ts):8.3f} ms  {P / min(ts) * 1e3:8.1f} params/s  "
+    print(f"C3 P={P} fft_full={full} fft_tc={tc} fft_pair={pair}: {min(ts):8.3f} ms  {P / min(ts) * 1e3:8.1f} params/s  "
           f"frac {P / min(ts) * 1e3 / 204631:.4f}  max rel diff vs first = {rel:.2e}", flush=True)
-ctx.set_option("fft_tc", 0); ctx.set_option("use_crank", 1); ctx.set_option("fft_full", 0)
+ctx.set_option("fft_tc", 0); ctx.set_option("fft_full", 0); ctx.set_option("fft_pair", 1)
+# other shapes of the paired path: odd chain count, N1 with a factor 3, Float32
+for (d, c, split, dt) in ((9001, 3, 1, "float64"), (30000, 1, 2, "float64"), (200000, 3, 2, "float32"), (70000, 5, 1, "float64")):
+    y = m.generate_ar1(0.7, np.sqrt(1 - 0.49), d, c, 6, seed=5, dtype=dt)
+    out = []
+    for pair in (0, 1):
+        ctx.set_option("fft_pair", pair)
+        out.append(m.ess(y, kind="bulk", autocov_method=m.FFTAutocovMethod(), split_chains=split).double())
+    direct = m.ess(y, kind="bulk", split_chains=split).double()
+    print(f"{d}x{c} split={split} {dt}: pair vs per-chain max rel diff {float(((out[0] - out[1]).abs() / out[0].abs()).max()):.2e}; "
+          f"FFT vs direct {float(((out[1] - direct).abs() / direct.abs()).max()):.2e}", flush=True)
+ctx.set_option("fft_pair", 1)
