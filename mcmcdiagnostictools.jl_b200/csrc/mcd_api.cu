@@ -65,6 +65,7 @@ struct mcd_ctx {
   int fft_tc = 0;          // developer knob: columns per tile of the four-step FFT (0 = default)
   int fft_full = 0;        // developer knob: 1 = FFT length nextprod(2 niter - 1) (default: niter + maxlag)
   int fft_pair = 1;        // developer knob: 0 = four-step FFT with one transform per chain (round-1 data flow)
+  int ztab_max_mb = 32;    // the counting rank looks z up in the ztab table while the table is at most this large
   // stats
   long long crank_chunks = 0, crank_fallbacks = 0;
   long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -371,7 +372,7 @@ static size_t slab_layout(SlabArgs<T>& a, const Program& pg, int threads = SLAB_
   a.offPART = take(part * 8);
   a.offFFT = a.offK;
   if (pg.method == MCD_AUTOCOV_FFT && pg.want_ess) {
-    size_t need = (size_t)a.fft_n * 2 * 2 * ts;
+    size_t need = (size_t)a.fft_n * (2 * 2 + 1) * ts;   // two complex buffers + the summed power spectrum
     if (need > view_bytes) a.offFFT = take(need);
   }
   a.offMISC = take(sizeof(Misc));
@@ -738,7 +739,7 @@ static int run_device(mcd_ctx* ctx, const T* dx, long long params, const SplitGe
   env.fft_tc = ctx->fft_tc; env.fft_full = ctx->fft_full; env.fft_pair = ctx->fft_pair;
   env.crank_chunks = &ctx->crank_chunks; env.crank_fallbacks = &ctx->crank_fallbacks;
   // the counting rank turns ranks into z by a table lookup while the table stays cache-sized (<= 32 MB)
-  if (ctx->use_crank && g.n >= 1024 && (size_t)g.n * 4 * sizeof(T) <= ((size_t)32 << 20)) {
+  if (ctx->use_crank && g.n >= 1024 && (size_t)g.n * 4 * sizeof(T) <= ((size_t)ctx->ztab_max_mb << 20)) {
     const int zrc = ensure_ztab(ctx, sizeof(T) == 8 ? MCD_F64 : MCD_F32, g.n);
     if (zrc) return zrc;
     env.ztab = ctx->ztab;
@@ -1252,6 +1253,7 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   else if (k == "use_big") { ctx->use_big = (int)value; }
   else if (k == "use_crank") { ctx->use_crank = (int)value; }
   else if (k == "crank_factor") { if (value < 1 || value > 64) return fail(ctx, MCD_EINVAL, "crank_factor in 1..64"); ctx->crank_factor = (int)value; }
+  else if (k == "ztab_max_mb") { if (value < 0 || value > 4096) return fail(ctx, MCD_EINVAL, "ztab_max_mb in 0..4096"); ctx->ztab_max_mb = (int)value; }
   else if (k == "fft_pair") { ctx->fft_pair = value ? 1 : 0; }
   else if (k == "fft_full") { ctx->fft_full = value ? 1 : 0; }
   else if (k == "fft_tc") { if (value < 0 || value > 4) return fail(ctx, MCD_EINVAL, "fft_tc in 0..4"); ctx->fft_tc = (int)value; }

@@ -384,6 +384,21 @@ __global__ void __launch_bounds__(LG_THREADS) chain_stats_group_kernel(const T* 
   if (live && l == 0) { cm[wid] = m; cv[wid] = (T)(q / (double)(g.niter - 1)); }
 }
 
+// ---- FFT autocovariance, one CTA per PARAMETER: chains paired, spectra summed, one inverse (fft_autocov_summed) ----
+template <typename T>
+__global__ void __launch_bounds__(LG_THREADS) fft_param_kernel(const T* __restrict__ Y, SplitGeom g, const T* __restrict__ cm,
+                                                               int N, const Cx<T>* __restrict__ tw, int maxlag,
+                                                               T* __restrict__ ac) {
+  extern __shared__ __align__(16) unsigned char smem_fft[];
+  Cx<T>* fa = reinterpret_cast<Cx<T>*>(smem_fft);
+  Cx<T>* fb = fa + N;
+  T* P = reinterpret_cast<T*>(fb + N);
+  const long long param = blockIdx.x;
+  Cx<T>* r = fft_autocov_summed<T, LG_THREADS>(Y + param * (long long)g.n, g, cm + param * g.nch, fa, fb, P, N, tw);
+  T* dst = ac + param * (long long)(maxlag + 1);
+  for (int k = threadIdx.x; k <= maxlag; k += LG_THREADS) dst[k] = r[k].x;   // summed raw Re c[k]; the ratio is formed later
+}
+
 // ---- FFT autocovariance, one CTA per (parameter, chain), shared-memory Stockham ------------------
 template <typename T>
 __global__ void __launch_bounds__(LG_THREADS) fft_chain_kernel(const T* __restrict__ Y, SplitGeom g,
@@ -668,9 +683,13 @@ __global__ void __launch_bounds__(LG_THREADS) ess_kernel(const EssArgs<T> a) {
   if (a.method == 1 && a.ac_summed) {
     // one series per parameter: sum over the chains of the raw Re c[k] (paired four-step FFT).  mean_i(c[k,i] /
     // c[0,i] var_i) with c[0,i] = (niter - 1) var_i is (sum_i c[k,i] / sum_i c[0,i]) mean_i(var_i)
+    // (a chain whose centred values are all exactly zero has c[0,i] = 0: the reference's term is 0 / 0 = NaN)
     const T* ac = a.ac + param * (long long)(maxlag + 1);
     const T unc = (T)(niter - 1) / (T)niter;
-    for (int k = threadIdx.x; k <= maxlag; k += LG_THREADS) gamma[k] = (ac[k] / ac[0]) * W * unc;
+    int deg = 0;
+    for (int j = threadIdx.x; j < g.nch; j += LG_THREADS) deg |= (cv[j] == (T)0);
+    deg = __syncthreads_or(deg);
+    for (int k = threadIdx.x; k <= maxlag; k += LG_THREADS) gamma[k] = (deg ? Traits<T>::nan() : ac[k] / ac[0]) * W * unc;
     __syncthreads();
     have = maxlag;
   } else if (a.method == 1) {
@@ -913,6 +932,8 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
   // paired variant: three N2-point complex buffers + N2 powers per CTA of the row kernel
   const bool fft_pair = fft_big && env.fft_pair && (size_t)fN2 * 7 * ts + 1024 <= (size_t)env.smem_optin;
   const int npair = (g.nch + 1) / 2;
+  // chains that fit shared memory: one CTA per parameter with paired chains and one inverse, if N reals more fit
+  const bool fft_smem_pair = use_fft && !fft_big && env.fft_pair && (size_t)fftN * 5 * ts + 1024 <= (size_t)env.smem_optin;
   const long long fft_bufs = fft_pair ? npair : g.nch;   // N-point complex buffers per parameter
   const long long nan_tiles = (n + NAN_TILE - 1) / NAN_TILE;
   const long long gam_stride = maxlag + 1 + LAG_BATCH;
@@ -1003,6 +1024,7 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
     twiddle_kernel_l<T><<<(unsigned)((fftN + 255) / 256), 256, 0, st>>>(tw, (int)fftN);
     LAUNCHED();
     LCU(cudaFuncSetAttribute(fft_chain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fftN * 4 * ts)));
+    if (fft_smem_pair) LCU(cudaFuncSetAttribute(fft_param_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fftN * 5 * ts)));
   }
   if (fft_big) {
     twiddle_stride_kernel<T><<<(unsigned)((fN1 + 255) / 256), 256, 0, st>>>(tw1, fN1, 1, (int)fN1); LAUNCHED();
@@ -1192,7 +1214,8 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
         } else {
           const bool want_ess = stp.reduce == RD_ESS_RHAT;
           if (want_ess && use_fft && !fft_big) {
-            fft_chain_kernel<T><<<(unsigned)nwork, LG_THREADS, (size_t)fftN * 4 * ts, st>>>(proxy, g, cm, cv, (int)fftN, tw, maxlag, ac);
+            if (fft_smem_pair) fft_param_kernel<T><<<(unsigned)pc, LG_THREADS, (size_t)fftN * 5 * ts, st>>>(proxy, g, cm, (int)fftN, tw, maxlag, ac);
+            else fft_chain_kernel<T><<<(unsigned)nwork, LG_THREADS, (size_t)fftN * 4 * ts, st>>>(proxy, g, cm, cv, (int)fftN, tw, maxlag, ac);
             LAUNCHED();
           }
           if (want_ess && fft_big) {
@@ -1224,7 +1247,7 @@ static int run_large(LargeEnv& env, const T* dx, long long params, const SplitGe
           ea.Y = proxy; ea.g = g; ea.params = pc; ea.cm = cm; ea.cv = cv;
           ea.want_ess = want_ess; ea.method = method; ea.maxlag = maxlag; ea.relative = relative; ea.ess_nan = ess_nan;
           ea.rel_ess_max = rel_ess_max; ea.gam = gam; ea.ac = ac; ea.r_ess = r_ess; ea.r_rhat = r_rhat;
-          ea.ac_summed = want_ess && fft_big && fft_pair;
+          ea.ac_summed = want_ess && ((fft_big && fft_pair) || fft_smem_pair);
           ess_kernel<T><<<(unsigned)pc, LG_THREADS, 0, st>>>(ea);
           LAUNCHED();
         }

@@ -541,34 +541,58 @@ __device__ Cx<T>* fft_block(Cx<T>* a, Cx<T>* b, int N, const Cx<T>* __restrict__
 }
 
 // gamma[0..maxlag] with the FFT estimator (ess_rhat.jl:130-152, 181-195) on centred samples.
+// Summed raw autocorrelation of the chains of one parameter through ONE inverse transform (block-wide, in shared
+// memory).  Chains are real: chains 2q and 2q+1 ride one complex transform z = a + i b, |A(k)|^2 + |B(k)|^2 =
+// (|Z(k)|^2 + |Z(N-k)|^2) / 2; the power spectra of all chains are summed in P and inverted once (the transform is
+// linear, and only the chain average is ever used: mean_autocov, ess_rhat.jl:181-195).  nch / 2 + 1 transforms
+// instead of 2 nch.  `cm` = chain means to subtract on load, or null when Y is already centred.  fa, fb: N complex
+// each; P: N reals.  Returns the buffer whose real parts are N * sum_j c_j[k] (the scale cancels in the callers'
+// ratio c[k] / c[0]).
 template <typename T, int THREADS>
-__device__ void fft_autocov(const T* Y, const SplitGeom& g, int maxlag, const T* cvar, Cx<T>* fa,
-                            Cx<T>* fb, int N, const Cx<T>* tw, double* gsum, T* gamma) {
+__device__ Cx<T>* fft_autocov_summed(const T* Y, const SplitGeom& g, const T* cm, Cx<T>* fa, Cx<T>* fb, T* P, int N,
+                                     const Cx<T>* tw) {
   const int tid = threadIdx.x;
-  for (int k = tid; k <= maxlag; k += THREADS) gsum[k] = 0.0;
-  __syncthreads();
-  for (int j = 0; j < g.nch; ++j) {
-    const T* p = Y + g.chain_start(j);
+  for (int t = tid; t < N; t += THREADS) P[t] = (T)0;
+  for (int ja = 0; ja < g.nch; ja += 2) {
+    const bool hasb = ja + 1 < g.nch;
+    const T* pa = Y + g.chain_start(ja);
+    const T* pb = hasb ? Y + g.chain_start(ja + 1) : pa;
+    const T ma = cm ? cm[ja] : (T)0, mb = (cm && hasb) ? cm[ja + 1] : (T)0;
     for (int t = tid; t < N; t += THREADS) {
-      Cx<T> c; c.x = t < g.niter ? p[t] : (T)0; c.y = (T)0;
+      Cx<T> c;
+      c.x = t < g.niter ? (T)(pa[t] - ma) : (T)0;
+      c.y = (hasb && t < g.niter) ? (T)(pb[t] - mb) : (T)0;
       fa[t] = c;
     }
     __syncthreads();
     Cx<T>* f = fft_block<T, THREADS>(fa, fb, N, tw, false);
-    Cx<T>* o = (f == fa) ? fb : fa;
     for (int t = tid; t < N; t += THREADS) {
-      Cx<T> c = f[t];
-      c.x = c.x * c.x + c.y * c.y; c.y = (T)0;
-      f[t] = c;
+      const Cx<T> u = f[t], v = f[t == 0 ? 0 : N - t];
+      P[t] += (T)0.5 * ((u.x * u.x + u.y * u.y) + (v.x * v.x + v.y * v.y));
     }
     __syncthreads();
-    Cx<T>* r = fft_block<T, THREADS>(f, o, N, tw, true);
-    const T c0 = r[0].x, v = cvar[j];
-    for (int k = tid; k <= maxlag; k += THREADS) gsum[k] += (double)((r[k].x / c0) * v);
-    __syncthreads();
   }
+  for (int t = tid; t < N; t += THREADS) { Cx<T> c; c.x = P[t]; c.y = (T)0; fa[t] = c; }
+  __syncthreads();
+  return fft_block<T, THREADS>(fa, fb, N, tw, true);
+}
+
+// mean_autocov of FFTAutocovMethod (ess_rhat.jl:181-195) for the centred slab Y: gamma[k] =
+// mean_i(c[k,i] / c[0,i] var_i) (niter - 1) / niter.  With c[0,i] = (niter - 1) var_i (the chain's own lag-0 term)
+// this is (sum_i c[k,i] / sum_i c[0,i]) W (niter - 1) / niter, W = mean_i(var_i): formed from the summed series.
+// A chain whose centred values are all exactly zero (a constant chain, e.g. a tail indicator that never fires) has
+// c[0,i] = 0 and makes the reference's term 0 / 0 = NaN: the summed form keeps that by checking the chain variances.
+template <typename T, int THREADS>
+__device__ void fft_autocov(const T* Y, const SplitGeom& g, int maxlag, T W, const T* cvar, Cx<T>* fa,
+                            Cx<T>* fb, int N, const Cx<T>* tw, T* gamma) {
+  const int tid = threadIdx.x;
+  int deg = 0;
+  for (int j = tid; j < g.nch; j += THREADS) deg |= (cvar[j] == (T)0);
+  deg = __syncthreads_or(deg);
+  Cx<T>* r = fft_autocov_summed<T, THREADS>(Y, g, nullptr, fa, fb, reinterpret_cast<T*>(fb + N), N, tw);
   const T unc = (T)(g.niter - 1) / (T)g.niter;
-  for (int k = tid; k <= maxlag; k += THREADS) gamma[k] = (T)(gsum[k] / (double)g.nch) * unc;
+  const T c0 = deg ? (T)0 : r[0].x;
+  for (int k = tid; k <= maxlag; k += THREADS) gamma[k] = (deg ? Traits<T>::nan() : r[k].x / c0) * W * unc;
   __syncthreads();
 }
 
@@ -603,10 +627,9 @@ __device__ Result reduce_ess_rhat(T* Y, const SlabArgs<T>& a, unsigned char* sme
   const int maxlag = a.maxlag;
   int have = 0;  // lags 1..have are in gamma[]
   if (a.method == 1) {
-    fft_autocov<T, THREADS>(Y, g, maxlag, cvar, reinterpret_cast<Cx<T>*>(smem + a.offFFT),
+    fft_autocov<T, THREADS>(Y, g, maxlag, W, cvar, reinterpret_cast<Cx<T>*>(smem + a.offFFT),
                             reinterpret_cast<Cx<T>*>(smem + a.offFFT) + a.fft_n, a.fft_n,
-                            reinterpret_cast<const Cx<T>*>(a.twiddle),
-                            reinterpret_cast<double*>(smem + a.offGSUM), gamma);
+                            reinterpret_cast<const Cx<T>*>(a.twiddle), gamma);
     have = maxlag;
   }
   const T inv_var_plus = (T)1 / var_plus;

@@ -38,3 +38,33 @@ for (d, c, split, dt) in ((9001, 3, 1, "float64"), (30000, 1, 2, "float64"), (20
     print(f"{d}x{c} split={split} {dt}: pair vs per-chain max rel diff {float(((out[0] - out[1]).abs() / out[0].abs()).max()):.2e}; "
           f"FFT vs direct {float(((out[1] - direct).abs() / direct.abs()).max()):.2e}", flush=True)
 ctx.set_option("fft_pair", 1)
+
+# ---- shared-memory FFT paths (slab kernel; large path with chains that fit shared memory) ----------------------
+def t_ms(f, reps=3):
+    f(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); f(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts)
+
+xh = m.generate_ar1(0.5, np.sqrt(0.75), 1000, 4, 200_000, seed=1)
+f_fft = lambda: m.ess_rhat(xh, kind="basic", autocov_method=m.FFTAutocovMethod())
+d = m.ess_rhat(xh, kind="basic")[0].double(); f = f_fft()[0].double()
+print(f"headline shape, FFT method (slab kernel): {t_ms(f_fft):.2f} ms per 200k (round 1: 97.3); FFT vs direct max rel diff "
+      f"{float(((f - d).abs() / d.abs()).max()):.2e}", flush=True)
+ym = m.generate_ar1(0.6, 0.8, 6000, 4, 2000, seed=2)
+for pair in (0, 1):
+    ctx.set_option("fft_pair", pair)
+    ff = lambda: m.ess(ym, kind="bulk", autocov_method=m.FFTAutocovMethod())
+    r = ff().double()
+    if pair == 0:
+        r0 = r
+    print(f"6000x4 x 2000 params, FFT in shared memory per chain / per parameter (fft_pair={pair}): {t_ms(ff):.2f} ms, path {ctx.stat('last_path')}, "
+          f"max rel diff vs per-chain {float(((r - r0).abs() / r0.abs()).max()):.2e}", flush=True)
+ctx.set_option("fft_pair", 1)
+for mb in (32, 160):
+    ctx.set_option("ztab_max_mb", mb)
+    print(f"C3 P={P} z table up to {mb} MB: {t_ms(fn, 2):.3f} ms", flush=True)
+ctx.set_option("ztab_max_mb", 32)
