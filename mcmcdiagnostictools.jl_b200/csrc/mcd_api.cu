@@ -92,6 +92,25 @@ static int fail(mcd_ctx* c, int code, const char* fmt, ...) {
                   #call, cudaGetErrorString(e_));                                             \
   } while (0)
 
+// The library switches the calling thread's current CUDA device to the context's device for the duration of an entry
+// point and restores it on return: a host application (torch, CUDA.jl, ...) keeps whatever device it had selected.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) {
+      err = cudaSetDevice(dev);
+      changed = err == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_DEVICE(c_) DeviceGuard dev_guard_((c_)->device); CU(dev_guard_.err)
+
 static int ensure_cap(mcd_ctx* ctx, void** p, size_t* cap, size_t need) {
   if (*cap >= need && *p) return MCD_OK;
   if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
@@ -801,7 +820,7 @@ static int execute_jobs_t(mcd_ctx* ctx, const void* x, int mem, long long draws,
   if (params > 0 && !x) return fail(ctx, MCD_EINVAL, "x is NULL");
   SplitGeom g((int)draws, (int)chains, split);
   const long long n = g.n;
-  CU(cudaSetDevice(ctx->device));
+  ON_DEVICE(ctx);
   CU(cudaMemsetAsync(ctx->d_flags, 0, sizeof(unsigned), ctx->stream));
   bool can_raise = false;   // flags are only consulted for programs that can raise an error
   for (int j = 0; j < njobs; ++j) {
@@ -950,7 +969,7 @@ static int fill_skipped(mcd_ctx* ctx, int mem, void* out, long long lo, long lon
   const T nanv = std::numeric_limits<T>::quiet_NaN();
   if (mem == MCD_HOST) { for (long long i = 0; i < cnt; ++i) o[i] = nanv; return MCD_OK; }
   mcd_ctx* c = ctx->children.empty() ? ctx : ctx->children[0];
-  CU(cudaSetDevice(c->device));
+  DeviceGuard dev_guard_c_(c->device); CU(dev_guard_c_.err);
   fill_kernel<T><<<(unsigned)std::min<long long>((cnt + 255) / 256, 4096), 256, 0, c->stream>>>(o, cnt, nanv);
   CU(cudaGetLastError());
   return MCD_OK;
@@ -1031,7 +1050,7 @@ static int chain_moments_t(mcd_ctx* ctx, const void* x, int mem, long long draws
                            int split, void* mean_out, void* var_out) {
   SplitGeom g((int)draws, (int)chains, split);
   if (g.niter < 1) return fail(ctx, MCD_EINVAL, "fewer draws than split chains");
-  CU(cudaSetDevice(ctx->device));
+  ON_DEVICE(ctx);
   auto launch = [&](const T* dx, long long cnt, T* dm, T* dv) -> int {
     const long long warps = cnt * g.nch;
     const unsigned grid = (unsigned)std::min<long long>((warps + 7) / 8, (long long)ctx->sm_count * 32);
@@ -1068,7 +1087,7 @@ static int chain_moments_t(mcd_ctx* ctx, const void* x, int mem, long long draws
 
 template <typename T>
 static int bfmi_t(mcd_ctx* ctx, const void* e, int mem, long long draws, long long chains, void* out) {
-  CU(cudaSetDevice(ctx->device));
+  ON_DEVICE(ctx);
   const T* de = (const T*)e;
   T* dout = (T*)out;
   const size_t bytes = (size_t)draws * chains * sizeof(T);
@@ -1118,7 +1137,8 @@ int mcd_create(mcd_ctx** out, int device) {
     delete ctx;
     return MCD_ECUDA;
   };
-  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  DeviceGuard dev_guard_(device);
+  if ((e = dev_guard_.err) != cudaSuccess) return bail("cudaSetDevice", e);
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
   if (prop.major < 10) {
@@ -1173,7 +1193,7 @@ void mcd_destroy(mcd_ctx* ctx) {
     delete ctx;
     return;
   }
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard_(ctx->device);
   cudaDeviceSynchronize();
   void* ptrs[] = {ctx->ztab, ctx->tw, ctx->d_flags, ctx->d_chain_inds, ctx->d_redo, ctx->stage[0], ctx->stage[1],
                   ctx->d_out, ctx->d_arr, ctx->work};
@@ -1201,7 +1221,7 @@ int mcd_set_stream(mcd_ctx* ctx, void* cuda_stream, int use_own) {
   if (next != ctx->stream) {
     // Every call shares the context's scratch (status flags, redo list, cached z / twiddle tables, workspace):
     // work queued on the new stream must not start before the work already queued on the old one is done.
-    CU(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (!ctx->ev_switch) CU(cudaEventCreateWithFlags(&ctx->ev_switch, cudaEventDisableTiming));
     CU(cudaEventRecord(ctx->ev_switch, ctx->stream));
     CU(cudaStreamWaitEvent(next, ctx->ev_switch, 0));
@@ -1217,7 +1237,7 @@ int mcd_synchronize(mcd_ctx* ctx) {
     return MCD_OK;
   }
   std::lock_guard<std::mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device));
+  ON_DEVICE(ctx);
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->copy_stream));
   return MCD_OK;
@@ -1285,7 +1305,7 @@ int64_t mcd_get_stat(const mcd_ctx* ctx, const char* key) {
   if (k == "redo_count") {   // parameters the register-resident kernel handed to the general kernel in the last call (last chunk)
     if (!ctx->d_redo) return 0;
     int v = 0;
-    cudaSetDevice(ctx->device);
+    DeviceGuard dev_guard_(ctx->device);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
     if (cudaMemcpy(&v, ctx->d_redo, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return v;
@@ -1536,7 +1556,7 @@ int mcd_generate_ar1(mcd_ctx* ctx, int dtype, int64_t draws, int64_t chains, int
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->err.clear();
   if (!dev_x || draws <= 0 || chains <= 0 || params < 0) return fail(ctx, MCD_EINVAL, "bad argument");
-  CU(cudaSetDevice(ctx->device));
+  ON_DEVICE(ctx);
   long long series = chains * params;
   if (series == 0) return MCD_OK;
   long long blocks = (series + 127) / 128;
@@ -1554,7 +1574,7 @@ int mcd_device_alloc(mcd_ctx* ctx, int64_t bytes, void** dev_ptr) {
   if (!ctx || !dev_ptr || bytes < 0) return MCD_EINVAL;
   if (!ctx->children.empty()) { const int rc_ = mcd_device_alloc(ctx->children[0], bytes, dev_ptr); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device));
+  ON_DEVICE(ctx);
   CU(cudaMalloc(dev_ptr, (size_t)std::max<int64_t>(bytes, 1)));
   return MCD_OK;
 }
@@ -1562,7 +1582,7 @@ int mcd_device_free(mcd_ctx* ctx, void* dev_ptr) {
   if (!ctx) return MCD_EINVAL;
   if (!ctx->children.empty()) { const int rc_ = mcd_device_free(ctx->children[0], dev_ptr); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device));
+  ON_DEVICE(ctx);
   CU(cudaFree(dev_ptr));
   return MCD_OK;
 }
@@ -1570,7 +1590,7 @@ int mcd_memcpy_h2d(mcd_ctx* ctx, void* dev_dst, const void* host_src, int64_t by
   if (!ctx) return MCD_EINVAL;
   if (!ctx->children.empty()) { const int rc_ = mcd_memcpy_h2d(ctx->children[0], dev_dst, host_src, bytes); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device));
+  ON_DEVICE(ctx);
   CU(cudaMemcpyAsync(dev_dst, host_src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return MCD_OK;
@@ -1579,7 +1599,7 @@ int mcd_memcpy_d2h(mcd_ctx* ctx, void* host_dst, const void* dev_src, int64_t by
   if (!ctx) return MCD_EINVAL;
   if (!ctx->children.empty()) { const int rc_ = mcd_memcpy_d2h(ctx->children[0], host_dst, dev_src, bytes); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device));
+  ON_DEVICE(ctx);
   CU(cudaMemcpyAsync(host_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return MCD_OK;
@@ -1588,7 +1608,7 @@ int mcd_host_alloc(mcd_ctx* ctx, int64_t bytes, void** host_ptr) {
   if (!ctx || !host_ptr || bytes < 0) return MCD_EINVAL;
   if (!ctx->children.empty()) { const int rc_ = mcd_host_alloc(ctx->children[0], bytes, host_ptr); if (rc_) ctx->err = ctx->children[0]->err; return rc_; }
   std::lock_guard<std::mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device));
+  ON_DEVICE(ctx);
   CU(cudaHostAlloc(host_ptr, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
   return MCD_OK;
 }
