@@ -498,7 +498,7 @@ template <typename T>
 static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom& g, const Program& pg,
                     T* d_ess, T* d_rhat, bool* handled) {
   *handled = false;
-  if (g.nch != FAST_NCH || g.rem != 0 || g.niter < 2 || g.niter > FAST_MAXITER || params >= (1ll << 31)) return MCD_OK;
+  if (g.nch < 1 || g.nch > FAST_NCH || g.rem != 0 || g.niter < 2 || g.niter > FAST_MAXITER || params >= (1ll << 31)) return MCD_OK;
   if (pg.want_arr || pg.chain_inds) return MCD_OK;
   const bool ess_live = pg.want_ess && !pg.ess_nan;
   if (ess_live && pg.method != MCD_AUTOCOV_DIRECT) return MCD_OK;
@@ -516,6 +516,12 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
              pg.steps[1].reduce == RD_RHAT) {
     a.do_bulk = 1; a.rank_x = 1; a.want_ess = s0.reduce == RD_ESS_RHAT; a.do_tail = 1;
   } else lean = false;
+  // the TMA-staged kernel takes 1..8 split chains (a slab must be a whole number of 16-byte units for the bulk copy);
+  // the register-resident kernels exactly 8
+  const bool rk2_ok = lean && ctx->use_rk2 && ((uintptr_t)dx & 15u) == 0 && pg.maxlag <= RK_MAXLAG_CAP &&
+                      ((size_t)g.n * sizeof(T)) % 16 == 0;
+  if (g.nch != FAST_NCH && !rk2_ok) return MCD_OK;
+  a.nch = g.nch;
   FastGenArgs<T> ga;
   memset(&ga, 0, sizeof ga);
   if (!lean) {
@@ -575,7 +581,7 @@ static int run_fast(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   if (rc) return rc;
   a.redo_count = ga.redo_count = ctx->d_redo; a.redo_list = ga.redo_list = ctx->d_redo + 1;
   CU(cudaMemsetAsync(ctx->d_redo, 0, sizeof(int), ctx->stream));
-  if (lean && ctx->use_rk2 && ((uintptr_t)dx & 15u) == 0 && pg.maxlag <= RK_MAXLAG_CAP) {
+  if (rk2_ok) {
     // persistent CTAs, two per SM, each streaming its parameters through the bulk-copy pipeline
     const int mult = ctx->fast_grid_mult > 0 ? ctx->fast_grid_mult : 1;
     const unsigned grid = (unsigned)std::min<long long>(params, (long long)mult * 2 * ctx->sm_count);

@@ -69,7 +69,8 @@ __device__ __forceinline__ unsigned nibsum(unsigned w) {
 template <typename T> struct FastArgs {
   const T* x;
   long long params;
-  int niter;            // draws per split chain; n = 8 * niter
+  int niter;            // draws per split chain; n = nch * niter
+  int nch;              // split chains: 8 for fast_kernel / fastgen_kernel, 1..8 for rk2_kernel
   int rank_x;           // bulk step rank-normalises x (kind bulk / rank); 0 = basic
   int do_bulk;          // compute the bulk / basic step
   int want_ess;         // bulk step computes ESS

@@ -9,13 +9,18 @@ cudaError_t rk2_launch(const FastArgs<T>& a, unsigned grid, size_t extra_smem, c
   const int mode = (a.rank_x ? 1 : 0) | (a.do_bulk ? 2 : 0) | (a.do_tail ? 4 : 0);
   const bool lng = a.niter > 32 * (RK_EPT - 1);
   void (*kern)(const FastArgs<T>) = nullptr;
+  const bool full = a.nch == RK_NCH;
+#define RK2_PICK(M) kern = full ? (lng ? rk2_kernel<T, true, M, true> : rk2_kernel<T, false, M, true>) \
+                                : (lng ? rk2_kernel<T, true, M, false> : rk2_kernel<T, false, M, false>)
   switch (mode) {
-    case 7: kern = lng ? rk2_kernel<T, true, 7> : rk2_kernel<T, false, 7>; break;
-    case 3: kern = lng ? rk2_kernel<T, true, 3> : rk2_kernel<T, false, 3>; break;
-    case 2: kern = lng ? rk2_kernel<T, true, 2> : rk2_kernel<T, false, 2>; break;
-    case 4: kern = lng ? rk2_kernel<T, true, 4> : rk2_kernel<T, false, 4>; break;
+    case 7: RK2_PICK(7); break;
+    case 3: RK2_PICK(3); break;
+    case 2: RK2_PICK(2); break;
+    case 4: RK2_PICK(4); break;
     default: return cudaErrorInvalidValue;
   }
+#undef RK2_PICK
+  if (a.nch < 1 || a.nch > RK_NCH) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, RK_THREADS, smem, stream>>>(a);

@@ -111,12 +111,16 @@ __device__ __forceinline__ unsigned rk_group_sums(const uint4 c, unsigned& a, un
 
 // MODE: bit 0 = the bulk series is rank-normalised (else x itself: kind basic), bit 1 = bulk / basic step,
 // bit 2 = tail step (fold + rank-normalise + R-hat).  rank = 7, bulk = 3, basic = 2, tail R-hat = 4.
-template <typename T, bool LONG, int MODE>
+// FULL = exactly 8 split chains (the canonical 4 chains x 2 halves).  Otherwise a.nch in 1..7 split chains: the warps
+// without a chain hold no values (their slots are never live, their rows are zero) and still take part in the
+// ranking's block-wide phases; every count that depends on the number of chains uses nch.
+template <typename T, bool LONG, int MODE, bool FULL>
 __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a) {
   constexpr bool RANKX = (MODE & 1) != 0, BULK = (MODE & 2) != 0, TAIL = (MODE & 4) != 0;
   extern __shared__ __align__(128) unsigned char smem[];
   const int niter = a.niter;
-  const int n = RK_NCH * niter;
+  const int nch = FULL ? RK_NCH : a.nch;
+  const int n = nch * niter;
   T* XS = reinterpret_cast<T*>(smem + RK_OFF_XS);
   T* S = XS + 2;
   unsigned char* A = smem + RK_OFF_A;
@@ -143,7 +147,8 @@ __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a)
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const bool last_live = lane + 32 * (RK_EPT - 1) < niter;
-  auto live = [&](int k) -> bool { return LONG ? (k < RK_EPT - 1 || last_live) : (lane + 32 * k < niter); };
+  const bool has_chain = FULL || w < nch;
+  auto live = [&](int k) -> bool { return has_chain && (LONG ? (k < RK_EPT - 1 || last_live) : (lane + 32 * k < niter)); };
 
   const unsigned xs_addr = smem_u32(XS), mbar = smem_u32(mbar_ptr);
   const unsigned slab_bytes = (unsigned)n * (unsigned)sizeof(T);
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a)
 
       // ---- R-hat (ess_rhat.jl:387-408): warp 0 forms W and var_plus, thread 0 the ratios ----
       SplitGeom g8;
-      g8.niter = niter; g8.nch = RK_NCH;
+      g8.niter = niter; g8.nch = nch;
       T W = (T)0, var_plus = (T)1;
       if (w == 0) {
         if (TAIL) {
@@ -620,7 +625,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a)
               double sum = 0.0;
 #pragma unroll
               for (int i = 0; i < RK_NCH; ++i) sum += part[i * RK_LAGS + tid];
-              const T gk = (T)(sum / (double)RK_NCH) / (T)niter;
+              const T gk = (T)(sum / (double)nch) / (T)niter;
               rhoa[k] = (T)1 - inv_var_plus * (W - gk);   // rho_k (ess_rhat.jl:556,566-567)
             }
           }
@@ -648,7 +653,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) rk2_kernel(const FastArgs<T> a)
               done = 1;
               const T tau = jl_max<T>((T)0, (T)2 * g_sum + jl_max<T>((T)0, g_even) - (T)1);
               T e = jl_min<T>((T)1 / tau, a.rel_ess_max);
-              if (!a.relative) e *= (T)(niter * RK_NCH);
+              if (!a.relative) e *= (T)(niter * nch);
               ess = (double)e;
             }
             *decision = done;

@@ -212,3 +212,39 @@ def test_other_chain_counts(mcd, o, shape, split):
     S, R = mcd.ess_rhat(x32, split_chains=split)
     So, Ro = o.ess_rhat(x32, split_chains=split)
     assert close(S, So, 3 * RTOL32) and close(R, Ro, RTOL32)
+
+
+@pytest.mark.parametrize("shape,split", [((1000, 2), 2), ((1000, 1), 2), ((1000, 3), 2), ((512, 7), 1), ((300, 1), 1), ((999, 2), 3),
+                                          ((64, 3), 2), ((10, 1), 2), ((1000, 5), 1)])
+@pytest.mark.parametrize("kind", ["rank", "bulk", "tail", "basic"])
+def test_fewer_than_eight_split_chains_on_the_staged_kernel(mcd, o, shape, split, kind):
+    """1..7 split chains of <= 512 draws run on the TMA-staged kernel too (warps without a chain idle) whenever a slab
+    is a whole number of 16-byte units; results against the oracle and against the general kernel (which sums the
+    lagged products in another order: 1e-10)."""
+    x = o.ar1(0.6, 0.8, shape[0], shape[1], 9, rng=rng(58))
+    x[:3, 0, 4] = x[3:6, 0, 4]                                    # a few ties
+    ctx = mcd.get_context(0)
+    n = shape[0] * shape[1]
+    fast_ok = shape[0] % split == 0 and shape[0] // split <= 512 and (n * 8) % 16 == 0
+    for maxlag in (250, 3):
+        S, R = mcd.ess_rhat(x, kind=kind, split_chains=split, maxlag=maxlag)
+        if kind != "tail":
+            assert ctx.stat("last_path") == (3 if fast_ok else 1)
+        So, Ro = o.ess_rhat(x, kind=kind, split_chains=split, maxlag=maxlag)
+        assert close(S, So, RTOL64), (maxlag, S, So)
+        assert close(R, Ro, RTOL64)
+    Rr = mcd.rhat(x, kind=kind, split_chains=split)
+    assert close(Rr, o.rhat(x, kind=kind, split_chains=split), RTOL64)
+    if kind in ("rank", "bulk", "basic"):
+        S3, R3 = mcd.ess_rhat(x, kind=kind, split_chains=split)
+        ctx.set_option("force_path", 1)
+        try:
+            S1, R1 = mcd.ess_rhat(x, kind=kind, split_chains=split)
+        finally:
+            ctx.set_option("force_path", 0)
+        assert close(S3, S1, 1e-10) and close(R3, R1, 1e-12)
+    xf = x.astype(np.float32)
+    if (n * 4) % 16 == 0:
+        Sf, Rf = mcd.ess_rhat(xf, kind=kind, split_chains=split)
+        Sof, Rof = o.ess_rhat(xf, kind=kind, split_chains=split)
+        assert close(Sf, Sof, 1e-4) and close(Rf, Rof, 1e-4)
