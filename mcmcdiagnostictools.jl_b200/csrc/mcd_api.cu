@@ -56,6 +56,7 @@ struct mcd_ctx {
   int bucket_limit = 64;
   int fast_pad_smem = 0;   // developer knob: extra dynamic shared memory (lowers CTAs/SM)
   int slab_wide = 1;       // developer knob: 512-thread general kernel for slabs that fit one CTA per SM only
+  int slab_three = 1;      // developer knob: 0 = never use the 80-register entry (three CTAs per SM) of the general kernel
   int fast_grid_mult = 0;  // developer knob: 0 = one CTA per parameter, k = persistent grid of k * 2 * SMs CTAs
   int use_rk2 = 1;         // developer knob: 0 = round-1 register-resident kernel instead of the TMA-staged one
   int use_big = 1;         // developer knob: 0 = never use the big-slab estimator kernel (mcd_big.cuh)
@@ -453,7 +454,7 @@ static int run_slab(mcd_ctx* ctx, const T* dx, long long params, const SplitGeom
   }
   if (pg.chain_inds) a.chain_inds = ctx->d_chain_inds;
 
-  const bool three = 3 * (smem + 1024) <= (size_t)ctx->smem_optin + 1024;   // three CTAs of this slab fit an SM
+  const bool three = ctx->slab_three && 3 * (smem + 1024) <= (size_t)ctx->smem_optin + 1024;   // three CTAs of this slab fit an SM
   auto kern = threads == 512 ? slab_kernel_wide<T, 512> : (three ? slab_kernel<T, SLAB_THREADS> : slab_kernel_two<T, SLAB_THREADS>);
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long grid = std::min<long long>(params, 1ll << 30);
@@ -1285,6 +1286,7 @@ int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value) {
   else if (k == "fft_tc") { if (value < 0 || value > 4) return fail(ctx, MCD_EINVAL, "fft_tc in 0..4"); ctx->fft_tc = (int)value; }
   else if (k == "crank_chunk") { if (value < 0) return fail(ctx, MCD_EINVAL, "crank_chunk >= 0"); ctx->crank_chunk = value; }
   else if (k == "slab_wide") ctx->slab_wide = value ? 1 : 0;
+  else if (k == "slab_three") ctx->slab_three = value ? 1 : 0;
   else if (k == "sort_bucket_limit") { if (value < 0) return fail(ctx, MCD_EINVAL, "sort_bucket_limit >= 0"); ctx->bucket_limit = (int)value; }
   else return fail(ctx, MCD_EINVAL, "unknown option '%s'", key);
   return MCD_OK;
