@@ -172,7 +172,7 @@ CR_HD void cr_setup_body(const CrWork<T>& w, long long p) {
 // The per-element bodies below take a BATCH of CR_U elements (i0, i0 + stride, ... below i1): every load / atomic
 // of the batch is issued before the first dependent store, so a thread keeps CR_U random accesses in flight (the
 // compiler may not hoist the loads of one element over the stores of the previous one: the pointers may alias).
-constexpr int CR_U = 4;
+constexpr int CR_U = 4;   // (8 in flight measured no faster: 6.75 vs 6.64 ms on C4, P = 400)
 
 template <typename T>
 CR_HD void cr_count_body(const CrWork<T>& w, const T* x, long long n, long long p, long long i0, long long stride,
