@@ -105,7 +105,10 @@ int mcd_set_param_mask(mcd_ctx* ctx, const unsigned char* skip, int64_t params);
 
 /* Tuning / test knobs.  Keys: "force_path" (0 auto, 1 general shared-memory slab kernel,
  * 2 global-memory large-slab pipeline, 3 register-resident fast kernel only),
- * "h2d_chunk_bytes", "workspace_bytes", "sort_bucket_limit". */
+ * "h2d_chunk_bytes", "workspace_bytes", "sort_bucket_limit"; developer switches that select between equivalent
+ * implementations (results agree to rounding or exactly; used by the A/B scripts and the tests): "use_rk2",
+ * "use_big", "use_crank", "crank_factor", "crank_chunk", "ztab_max_mb", "fft_pair", "fft_full", "fft_tc",
+ * "slab_wide", "slab_three", "fast_grid_mult", "fast_pad_smem". */
 int mcd_set_option(mcd_ctx* ctx, const char* key, int64_t value);
 /* Counters.  Keys: "kernel_launches" (since creation), "last_path" (1 slab, 2 large, 3 fast),
  * "h2d_bytes", "d2h_bytes", "sm_count", "smem_optin", "ndev" (devices of the context), "redo_count" (parameters the register-resident
